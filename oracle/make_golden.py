@@ -142,9 +142,28 @@ def main():
         ("n250_noisy", 105, 250, 600, 800, "noisy", 0.25, 2),
         ("n400_ideal", 106, 400, 640, 480, "ideal", 0.15, 0),
         ("n600_split", 107, 600, 800, 600, "ideal", 0.15, 1),
+        # noisier scenes: >= 10 iterations, so the periodic split/merge paths run
+        ("n400_long", 206, 400, 800, 600, "ideal", 0.2, 3, 2.0),
+        ("n600_long", 204, 600, 800, 600, "ideal", 0.3, 2, 3.0),
+        ("n800_long", 203, 800, 800, 600, "ideal", 0.15, 0, 1.0),
     ]
-    for tag, seed, N, wd, ht, kind, ofrac, extra in cases:
-        sc = synth.make_scene(seed=seed, n_segments=N, width=wd, height=ht, outlier_frac=ofrac, extra_vps=extra)
+    split_calls = []
+    orig_split = vp.split_best_vp
+
+    def split_spy(i, v, s, **kw):
+        rec = {"v_in": v[i].copy(), "s_in": s.copy(), "w": kw["weightMatrix"].copy()}
+        r = orig_split(i, v, s, **kw)
+        rec["v_out"], rec["s_out"] = r["v"][i].copy(), r["s"].copy()
+        split_calls.append(rec)
+        return r
+
+    vp.split_best_vp = split_spy
+    for case in cases:
+        tag, seed, N, wd, ht, kind, ofrac, extra = case[:8]
+        noise = case[8] if len(case) > 8 else 0.5
+        split_calls.clear()
+        sc = synth.make_scene(seed=seed, n_segments=N, width=wd, height=ht, outlier_frac=ofrac,
+                              extra_vps=extra, noise_deg=noise)
         lp = sc["segments"].copy()
         lines = sc["lines"].copy()
         img = sphere_oracle.votes_to_image(sphere_oracle.sphere_votes(lines, S))
@@ -170,6 +189,16 @@ def main():
                             log=np.array(log))
         print("%s: N=%d iterations=%d VPs=%d counts=%s" % (tag, N, res["iterations"], res["vp"].shape[0],
                                                           res["counts"].astype(int).tolist()))
+        grew = [c for c in split_calls if c["v_out"].shape[0] > c["v_in"].shape[0]]
+        if tag == "n600_long" and grew:
+            c = grew[0]
+            ln = lines / np.linalg.norm(lines, axis=1, keepdims=True)
+            llen = np.array([vp.line_length(x) for x in lp])
+            with contextlib.redirect_stdout(io.StringIO()):
+                lwt = llen * np.clip(vp.line_rating_knn(lp, k2=4), 0.2, 1)
+            np.savez_compressed(os.path.join(args.out, "em_split_real_n600.npz"), lp=lp, l=ln, lweight=lwt,
+                                langles=vp.lines_angles(lp), **c)
+            print("  split vector: M %d -> %d" % (c["v_in"].shape[0], c["v_out"].shape[0]))
 
 
 if __name__ == "__main__":

@@ -116,3 +116,14 @@ def test_full_em(path):
     np.testing.assert_array_equal(res["vp_assoc"], g["vp_assoc"])
     np.testing.assert_allclose(res["sigma"], g["sigma"], rtol=1e-6)
     np.testing.assert_allclose(res["counts_weighted"], g["counts_weighted"], rtol=1e-9)
+
+
+def test_split_real(golden_dir):
+    """A split that really happened inside the reference's run of the n600_long scene."""
+    g = np.load(os.path.join(golden_dir, "em_split_real_n600.npz"))
+    v, s, added = vo.split_best_vp(g["v_in"].copy(), g["s_in"].copy(), g["lp"], g["l"], g["w"], g["lweight"],
+                                   g["langles"], 1e-3)
+    assert added == 1 and v.shape == g["v_out"].shape
+    ang = np.arccos(np.minimum(np.abs(np.sum(v * g["v_out"], axis=1)), 1.0))
+    assert ang.max() < 1e-7
+    np.testing.assert_allclose(s, g["s_out"], rtol=1e-12)
