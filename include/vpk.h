@@ -1,0 +1,166 @@
+/* vpk.h -- C ABI of the B200-native vanishing-point hot path (libvpk.so).
+ *
+ * Drop-in boundary for the lines -> sphere image -> CNN -> EM -> VPs path of
+ * fkluger/vanishing_points_2017.  Each entry point names the reference
+ * interface it replaces (file:line in the reference repository).  Plain
+ * pointers and sizes only; every function returns an int status (VPK_OK == 0)
+ * and never throws.  Unless a parameter is documented as a device pointer,
+ * buffers are HOST memory owned by the caller; the library stages them through
+ * device workspaces owned by the context.
+ *
+ * Ragged batches: image b owns rows offsets[b] .. offsets[b+1]-1 of the flat
+ * (sumN, 4) segment / (sumN, 3) line arrays (row-major float64, the dtype the
+ * reference's numpy arrays carry).
+ */
+#ifndef VPK_H
+#define VPK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VPK_API __attribute__((visibility("default")))
+#else
+#define VPK_API
+#endif
+
+#define VPK_ABI_VERSION 1
+#define VPK_MAX_VP 64   /* capacity of the per-image VP arrays in vpk_em_result   */
+#define VPK_GRID 20     /* CNN response grid, cnn/deploy.prototxt:283-296         */
+#define VPK_CNN_SIZE 500 /* CNN input side, cnn/deploy.prototxt:7                 */
+
+/* function status */
+enum { VPK_OK = 0, VPK_ERR_ARG = 1, VPK_ERR_CUDA = 2, VPK_ERR_STATE = 3, VPK_ERR_NOMEM = 4 };
+
+/* per-image EM status (the reference returns a dict of None instead,
+ * vp_localisation.py:205-206, 258-260, 402-404; no initial VP is an unhandled
+ * np.vstack([]) ValueError at :165) */
+enum { VPK_EM_OK = 0, VPK_EM_NO_INITIAL_VPS = 1, VPK_EM_NO_VPS_LEFT = 2, VPK_EM_CAPACITY = 3 };
+
+/* sphere-mapping formulation */
+enum { VPK_SPHERE_VOTES = 0,   /* pairwise-intersection vote histogram (north_star) */
+       VPK_SPHERE_CURVES = 1   /* reference geometry: great-circle coverage raster   */ };
+
+typedef struct vpk_ctx vpk_ctx;
+
+/* ---- context ------------------------------------------------------------ */
+/* replaces caffe.set_mode_gpu()/set_device(gpu_id), evaluation.py:20-21 */
+VPK_API int vpk_create(int device, vpk_ctx** out);
+VPK_API int vpk_destroy(vpk_ctx* ctx);
+VPK_API int vpk_abi_version(void);
+/* message of the last failing call on this thread ("" if none) */
+VPK_API const char* vpk_last_error(void);
+/* block until all work queued by this context has finished */
+VPK_API int vpk_synchronize(vpk_ctx* ctx);
+/* number of kernels this context has launched so far */
+VPK_API int64_t vpk_launch_count(const vpk_ctx* ctx);
+
+/* per-kernel device timing (CUDA events on the context's stream). */
+VPK_API int vpk_profile_enable(vpk_ctx* ctx, int enable);
+VPK_API int vpk_profile_reset(vpk_ctx* ctx);
+/* Returns the number of distinct kernels seen; fills up to `cap` entries. */
+VPK_API int vpk_profile_read(vpk_ctx* ctx, int cap, const char** names, double* total_ms, int64_t* launches);
+
+/* ---- S0: line construction ---------------------------------------------- */
+/* replaces the per-segment loop of evaluation.py:158-168 (and :199-209):
+ * lines[n] = [x1,y1,1] x [x2,y2,1]. */
+VPK_API int vpk_lines_from_segments(vpk_ctx* ctx, const double* segments, int64_t n, double* lines_out);
+
+/* ---- S1: sphere mapping ------------------------------------------------- */
+/* replaces sphere_mapping.sphere_line_plot (sphere_mapping.py:36-72) as
+ * reached through evaluation.get_sphere_image (evaluation.py:12-14).
+ *  mode VOTES : hist_out[b] (S*S uint32) = number of pairwise intersections
+ *               per cell, or, with `weights` (sumN float64, nullable),
+ *               whist_out[b] (S*S float32) = sum of Q.16-quantised w_i*w_j;
+ *               image_out[b] = floor(255*h/max h).
+ *  mode CURVES: hist_out[b] = number of lines whose sampled great circle covers
+ *               the pixel; image_out[b] = floor(255*(1-(1-alpha)^k)).
+ * Row 0 of every S*S plane is beta = +pi/2 (image orientation of the
+ * reference canvas); column 0 is alpha = -pi/2.  Any output may be NULL. */
+VPK_API int vpk_sphere_map(vpk_ctx* ctx, const double* lines, const int32_t* offsets, int32_t n_images,
+                   int32_t size, int32_t mode, double alpha, const double* weights,
+                   uint32_t* hist_out, float* whist_out, uint8_t* image_out);
+
+/* ---- C0/C1: CNN --------------------------------------------------------- */
+/* replaces evaluation.init_caffe (evaluation.py:17-22) + read_mean_blob
+ * (:25-31).  weights[k]/biases[k], k = 0..7, are float32 host arrays in Caffe
+ * blob layout for conv1..conv5, fc6, fc7, fc8_20x20 of cnn/deploy.prototxt
+ * ((out, in/group, kh, kw) resp. (out, in) row-major); mean is 500*500
+ * float32 or NULL (zeros). */
+VPK_API int vpk_cnn_load(vpk_ctx* ctx, const float* const* weights, const float* const* biases, const float* mean);
+/* replaces evaluation.caffe_forward (evaluation.py:34-38) for a batch:
+ * images (n, 500, 500) uint8 -> sigout (n, 20, 20) float32; logits_out
+ * (fc8 before the sigmoid) may be NULL. */
+VPK_API int vpk_cnn_forward(vpk_ctx* ctx, const uint8_t* images, int32_t n_images, float* sigout, float* logits_out);
+
+/* ---- E0..E12: EM --------------------------------------------------------- */
+/* keyword arguments of vp_localisation.expectation_maximisation
+ * (vp_localisation.py:168-172), same names and defaults */
+typedef struct vpk_em_config {
+    int32_t num_iter;           /* 100  */
+    int32_t num_init_vp;        /* 25   */
+    int32_t split_merge_freq;   /* 10   */
+    int32_t num_min_lines;      /* 3    */
+    int32_t do_merge;           /* 1    */
+    int32_t do_split;           /* 1    */
+    int32_t do_iterations;      /* 1    */
+    int32_t use_weights;        /* 1    */
+    double wbias;               /* 1    */
+    double merge_thresh;        /* 1e-3 */
+    double outlier_thresh;      /* 1.96^2 */
+    double final_convergence;   /* 5e-3 */
+    double s_thresh;            /* 1e-200 */
+} vpk_em_config;
+VPK_API void vpk_em_default_config(vpk_em_config* cfg);
+
+/* the reference's result dict (vp_localisation.py:441-442), flattened.
+ * All pointers are caller-owned host arrays; decision_metric may be NULL. */
+typedef struct vpk_em_result {
+    int32_t* status;          /* (B)               VPK_EM_*                         */
+    int32_t* n_vp;            /* (B)               rows of 'vp'                     */
+    int32_t* iterations;      /* (B)               'iterations'                     */
+    double* vp;               /* (B, VPK_MAX_VP, 3) 'vp'                            */
+    double* sigma;            /* (B, VPK_MAX_VP)    'sigma'                         */
+    int32_t* counts;          /* (B, VPK_MAX_VP)    'counts'                        */
+    double* counts_weighted;  /* (B, VPK_MAX_VP)    'counts_weighted'               */
+    int32_t* vp_assoc;        /* (sumN)             'vp_assoc' (-1 = outlier)       */
+    double* decision_metric;  /* (VPK_MAX_VP*sumN) or NULL: image b's (n_vp, N_b)
+                                 row-major block starts at VPK_MAX_VP*offsets[b]   */
+} vpk_em_result;
+
+/* replaces vp_localisation.expectation_maximisation (vp_localisation.py:
+ * 168-450) called per image by evaluation.run_em_single (evaluation.py:
+ * 344-347), for a ragged batch.  lines: (sumN,3) (normalised internally, the
+ * caller's array is not mutated); segments: (sumN,4); responses: (B,20,20)
+ * float64; sphere_images: (B,S,S) uint8; init_vp/init_vp_offsets: optional
+ * per-image initial VPs (the reference's init_vp kwarg) or NULL. */
+VPK_API int vpk_em(vpk_ctx* ctx, const double* lines, const double* segments, const int32_t* offsets,
+           int32_t n_images, const double* responses, const uint8_t* sphere_images, int32_t size,
+           const double* init_vp, const int32_t* init_vp_offsets,
+           const vpk_em_config* cfg, vpk_em_result* out);
+
+/* ---- whole path ---------------------------------------------------------- */
+/* example.py:37-39 / benchmark.py:59-66 for a ragged batch, without the
+ * per-image pickles: segments -> lines -> sphere image -> CNN -> EM, all
+ * intermediates staying in HBM.
+ *   vpk_pipeline_upload : host segments -> device-resident batch (H2D).
+ *   vpk_pipeline_run    : run the path on the resident batch (no H2D).
+ *   vpk_pipeline_fetch  : copy the results to host arrays (D2H).
+ *   vpk_pipeline_host   : the three in sequence (the end-to-end call).      */
+VPK_API int vpk_pipeline_upload(vpk_ctx* ctx, const double* segments, const int32_t* offsets, int32_t n_images);
+VPK_API int vpk_pipeline_run(vpk_ctx* ctx, int32_t size, int32_t sphere_mode, double alpha, const vpk_em_config* cfg);
+VPK_API int vpk_pipeline_fetch(vpk_ctx* ctx, vpk_em_result* out, float* sigout /* (B,20,20) or NULL */,
+                       uint8_t* sphere_images /* (B,S,S) or NULL */);
+VPK_API int vpk_pipeline_host(vpk_ctx* ctx, const double* segments, const int32_t* offsets, int32_t n_images,
+                      int32_t size, int32_t sphere_mode, double alpha, const vpk_em_config* cfg,
+                      vpk_em_result* out, float* sigout, uint8_t* sphere_images);
+/* device time of the last vpk_pipeline_run per stage: [lines+sphere, cnn, em, total] ms */
+VPK_API int vpk_pipeline_stage_ms(vpk_ctx* ctx, float ms[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPK_H */

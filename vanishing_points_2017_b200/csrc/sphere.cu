@@ -1,0 +1,432 @@
+// Stage S0 + S1: line construction and sphere mapping.
+//
+// Replaces the Python loop of reference evaluation.py:158-168 and
+// sphere_mapping.sphere_line_plot (sphere_mapping.py:36-72) with the index
+// maps of coordinate_conversion.py:4-61.
+//
+// All geometry is float64 with explicitly rounded operations (__dmul_rn & co,
+// never contracted into FMAs) in the same order as the numpy expressions the
+// reference evaluates, so that histogram bin indices are bit-exact against the
+// float64 CPU path; only asin/cos/atan/sincos can differ (by an ulp), which
+// moves a vote across a cell border with probability ~1e-13.
+//
+// Accumulation is integer (uint32 counts, or Q.16 fixed point in 64-bit for
+// weighted votes), so the result is independent of the order in which the
+// atomics land: deterministic without ordered accumulation.
+#include <math.h>
+#include "vpk_internal.cuh"
+
+namespace vpk {
+
+static constexpr int kTile = 128;            // lines per tile of the pair space
+static constexpr int kVoteThreads = 256;
+static constexpr int kNumSamples = 10000;    // sphere_mapping.py:40
+static constexpr int kLutMax = 4096;
+static constexpr double kPi = 3.141592653589793;   // == numpy.pi
+
+// ---------------------------------------------------------------------------
+// S0
+// ---------------------------------------------------------------------------
+__global__ void lines_from_segments_kernel(const double* __restrict__ seg, int64_t n, double* __restrict__ lines) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double2* s2 = reinterpret_cast<const double2*>(seg) + 2 * i;
+    double2 p1 = s2[0], p2 = s2[1];
+    // [x1,y1,1] x [x2,y2,1]   (evaluation.py:163-167, numpy.cross component order)
+    lines[3 * i + 0] = __dsub_rn(p1.y, p2.y);
+    lines[3 * i + 1] = __dsub_rn(p2.x, p1.x);
+    lines[3 * i + 2] = __dsub_rn(__dmul_rn(p1.x, p2.y), __dmul_rn(p1.y, p2.x));
+}
+
+int lines_from_segments_dev(vpk_ctx* ctx, const double* d_seg, int64_t n, double* d_lines) {
+    if (n <= 0) return VPK_OK;
+    KernelScope ks(ctx, "lines_from_segments");
+    lines_from_segments_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_seg, n, d_lines);
+    return check_launch("lines_from_segments");
+}
+
+// ---------------------------------------------------------------------------
+// shared index maps
+// ---------------------------------------------------------------------------
+// coordinate_conversion.py:29-30 followed by round-to-cell, clipped.
+__device__ __forceinline__ int angle_bin(double angle, double half_over_s, double s) {
+    double a = __dmul_rn(__dsub_rn(__dadd_rn(__ddiv_rn(angle, kPi), 0.5), half_over_s), s);
+    double r = floor(__dadd_rn(a, 0.5));
+    r = fmin(fmax(r, 0.0), s - 1.0);
+    return (int)r;
+}
+
+// ---------------------------------------------------------------------------
+// S1 votes
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool intersection_cell(double ax, double ay, double az, double bx, double by, double bz,
+                                                  double half_over_s, double s, int S, int& row, int& col) {
+    double px = __dsub_rn(__dmul_rn(ay, bz), __dmul_rn(az, by));
+    double py = __dsub_rn(__dmul_rn(az, bx), __dmul_rn(ax, bz));
+    double pz = __dsub_rn(__dmul_rn(ax, by), __dmul_rn(ay, bx));
+    double n = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)), __dmul_rn(pz, pz)));
+    if (!(n > 0.0) || isinf(n)) return false;
+    if (pz < 0.0) { px = -px; py = -py; }
+    double y = fmin(fmax(__ddiv_rn(py, n), -1.0), 1.0);
+    double beta = asin(y);
+    double inner = __ddiv_rn(__ddiv_rn(px, n), cos(beta));
+    if (isnan(inner)) return false;
+    inner = fmin(fmax(inner, -1.0), 1.0);
+    double alpha = asin(inner);
+    col = angle_bin(alpha, half_over_s, s);
+    row = (S - 1) - angle_bin(beta, half_over_s, s);
+    return true;
+}
+
+// One CTA per (image, tile_i, tile_j) work item of the upper-triangular pair
+// space.  Tiles are staged in shared memory as SoA (conflict-free for the
+// j-direction, broadcast for the i-direction).
+__global__ void __launch_bounds__(kVoteThreads)
+sphere_votes_kernel(const double* __restrict__ lines, const int32_t* __restrict__ offsets,
+                    const int4* __restrict__ work, int S, const double* __restrict__ weights,
+                    uint32_t* __restrict__ hist, unsigned long long* __restrict__ whist) {
+    __shared__ double sA[3][kTile], sB[3][kTile], sWA[kTile], sWB[kTile];
+    const int4 item = work[blockIdx.x];
+    const int b = item.x, ti = item.y, tj = item.z;
+    const int base = offsets[b];
+    const int N = offsets[b + 1] - base;
+    const int i0 = ti * kTile, j0 = tj * kTile;
+    for (int t = threadIdx.x; t < kTile; t += blockDim.x) {
+        int gi = i0 + t, gj = j0 + t;
+        bool vi = gi < N, vj = gj < N;
+        const double* li = lines + 3 * (int64_t)(base + (vi ? gi : 0));
+        const double* lj = lines + 3 * (int64_t)(base + (vj ? gj : 0));
+        sA[0][t] = li[0]; sA[1][t] = li[1]; sA[2][t] = li[2];
+        sB[0][t] = lj[0]; sB[1][t] = lj[1]; sB[2][t] = lj[2];
+        if (weights) {
+            sWA[t] = weights[base + (vi ? gi : 0)];
+            sWB[t] = weights[base + (vj ? gj : 0)];
+        }
+    }
+    __syncthreads();
+    const double s = (double)S;
+    const double half_over_s = __ddiv_rn(0.5, s);
+    const int64_t plane = (int64_t)b * S * S;
+    const int ni = min(kTile, N - i0), nj = min(kTile, N - j0);
+    for (int idx = threadIdx.x; idx < ni * kTile; idx += blockDim.x) {
+        int i = idx / kTile, j = idx % kTile;
+        if (j >= nj) continue;
+        if (i0 + i >= j0 + j) continue;           // i < j only
+        int row, col;
+        if (!intersection_cell(sA[0][i], sA[1][i], sA[2][i], sB[0][j], sB[1][j], sB[2][j], half_over_s, s, S, row, col))
+            continue;
+        int64_t cell = plane + (int64_t)row * S + col;
+        if (weights) {
+            double q = floor(__dadd_rn(__dmul_rn(__dmul_rn(sWA[i], sWB[j]), 65536.0), 0.5));
+            if (q > 0.0) atomicAdd(whist + cell, (unsigned long long)q);
+        } else {
+            atomicAdd(hist + cell, 1u);
+        }
+    }
+}
+
+// per-image maximum of the histogram (uint32 counts or Q.16 sums)
+template <typename T>
+__global__ void plane_max_kernel(const T* __restrict__ h, int64_t plane, unsigned long long* __restrict__ maxv) {
+    const int b = blockIdx.y;
+    const T* p = h + (int64_t)b * plane;
+    unsigned long long m = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < plane; i += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long v = (unsigned long long)p[i];
+        m = v > m ? v : m;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+        m = t > m ? t : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxv + b, m);
+}
+
+// image = floor(255*h/max) in exact integer arithmetic; optional float export
+template <typename T>
+__global__ void votes_image_kernel(const T* __restrict__ h, int64_t plane, const unsigned long long* __restrict__ maxv,
+                                   uint8_t* __restrict__ img, float* __restrict__ wout) {
+    const int b = blockIdx.y;
+    const unsigned long long m = maxv[b];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < plane; i += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long v = (unsigned long long)h[(int64_t)b * plane + i];
+        if (img) img[(int64_t)b * plane + i] = m ? (uint8_t)((v * 255ull) / m) : (uint8_t)0;
+        if (wout) wout[(int64_t)b * plane + i] = (float)((double)v * (1.0 / 65536.0));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// S1 curves (reference geometry)
+// ---------------------------------------------------------------------------
+// a_k of numpy.linspace(-pi/2, pi/2, 10000): k*step + start, last = stop.
+__device__ __forceinline__ double sample_alpha(int k, double step) {
+    if (k == kNumSamples - 1) return 0.5 * kPi;
+    return __dadd_rn(__dmul_rn((double)k, step), -0.5 * kPi);
+}
+
+// row of sample k for line (l0,l1,l2); -1 if beta is NaN   (sphere_mapping.py:61-63)
+__device__ __forceinline__ int sample_row(int k, double step, double l0, double l1, double l2,
+                                          double half_over_s, double s, int S) {
+    double sa, ca;
+    sincos(sample_alpha(k, step), &sa, &ca);
+    double g = __ddiv_rn(__dsub_rn(__dmul_rn(-l0, sa), __dmul_rn(l2, ca)), l1);
+    double beta = atan(g);
+    if (isnan(beta)) return -1;
+    return (S - 1) - angle_bin(beta, half_over_s, s);
+}
+
+// One CTA per line; thread c handles column c: the covered rows are the closed
+// interval [min,max] of the rows of the reference's samples in that column
+// plus the first sample of the next column.  beta(alpha) is monotone between
+// the stationary point alpha* = atan(l0/l2) and the ends, so only the end
+// samples and the samples bracketing alpha* need evaluating.  The interval is
+// recorded in a per-image difference array (+1 at rmin, -1 at rmax+1).
+__global__ void sphere_curves_kernel(const double* __restrict__ lines, const int32_t* __restrict__ offsets, int B, int S,
+                                     const int32_t* __restrict__ first, double f, int32_t* __restrict__ diff) {
+    const int64_t line = blockIdx.x;
+    __shared__ int s_img;
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = B;           // largest b with offsets[b] <= line
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (offsets[mid] <= line) lo = mid; else hi = mid;
+        }
+        s_img = lo;
+    }
+    __syncthreads();
+    const int b = s_img;
+    const double l0 = __dmul_rn(lines[3 * line + 0], f);      // sphere_mapping.py:55-56
+    const double l1 = __dmul_rn(lines[3 * line + 1], f);
+    const double l2 = lines[3 * line + 2];
+    const double s = (double)S;
+    const double half_over_s = __ddiv_rn(0.5, s);
+    const double step = __ddiv_rn(kPi, (double)(kNumSamples - 1));
+    const double astar = atan(l0 / l2);
+    int kstar = isnan(astar) ? -10 : (int)floor((astar + 0.5 * kPi) / step);
+    int32_t* d = diff + (int64_t)b * (S + 1) * S;
+    for (int c = threadIdx.x; c < S; c += blockDim.x) {
+        int k0 = first[c];
+        int k1 = min(first[c + 1], kNumSamples - 1);   // inclusive: next column's first sample
+        if (first[c + 1] <= k0) continue;
+        int rmin = S, rmax = -1;
+        auto take = [&](int k) {
+            int r = sample_row(k, step, l0, l1, l2, half_over_s, s, S);
+            if (r >= 0) { rmin = min(rmin, r); rmax = max(rmax, r); }
+        };
+        take(k0);
+        if (k1 > k0) take(k1);
+#pragma unroll
+        for (int e = -1; e <= 2; ++e) {
+            int k = kstar + e;
+            if (k > k0 && k < k1) take(k);
+        }
+        if (rmax >= rmin) {
+            atomicAdd(d + (int64_t)rmin * S + c, 1);
+            atomicAdd(d + (int64_t)(rmax + 1) * S + c, -1);
+        }
+    }
+}
+
+// column-wise running sum of the difference array -> counts, LUT -> uint8
+__global__ void curves_scan_kernel(const int32_t* __restrict__ diff, int B, int S, const uint8_t* __restrict__ lut,
+                                   uint32_t* __restrict__ counts, uint8_t* __restrict__ img) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= (int64_t)B * S) return;
+    int b = (int)(t / S), c = (int)(t % S);
+    const int32_t* d = diff + (int64_t)b * (S + 1) * S;
+    int run = 0;
+    for (int r = 0; r < S; ++r) {
+        run += d[(int64_t)r * S + c];
+        int64_t o = ((int64_t)b * S + r) * S + c;
+        if (counts) counts[o] = (uint32_t)run;
+        if (img) img[o] = lut[min(run, kLutMax)];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static int host_angle_bin(double angle, int S) {
+    volatile double a = angle / kPi;
+    a = a + 0.5;
+    a = a - 0.5 / S;
+    a = a * S;
+    double r = floor(a + 0.5);
+    if (r < 0) r = 0;
+    if (r > S - 1) r = S - 1;
+    return (int)r;
+}
+
+int sphere_map_dev(vpk_ctx* ctx, const double* d_lines, const int32_t* d_offsets, const int32_t* h_offsets,
+                   int32_t B, int32_t S, int32_t mode, double alpha, const double* d_weights,
+                   uint32_t* d_hist, unsigned long long* d_whist, uint8_t* d_img) {
+    const int64_t plane = (int64_t)S * S;
+    const int64_t sumN = h_offsets[B];
+    if (mode == VPK_SPHERE_VOTES) {
+        // work list of upper-triangular tile pairs
+        int64_t items = 0;
+        for (int b = 0; b < B; ++b) {
+            int64_t T = (h_offsets[b + 1] - h_offsets[b] + kTile - 1) / kTile;
+            items += T * (T + 1) / 2;
+        }
+        const bool weighted = d_weights != nullptr;
+        if (weighted) VPK_CUDA(cudaMemsetAsync(d_whist, 0, sizeof(unsigned long long) * plane * B, ctx->stream));
+        else VPK_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * plane * B, ctx->stream));
+        if (items > 0) {
+            VPK_TRY(ctx->h_stage.ensure(items * sizeof(int4)));
+            VPK_TRY(ctx->d_work.ensure(items * sizeof(int4)));
+            int4* w = ctx->h_stage.as<int4>();
+            int64_t k = 0;
+            for (int b = 0; b < B; ++b) {
+                int T = (h_offsets[b + 1] - h_offsets[b] + kTile - 1) / kTile;
+                for (int ti = 0; ti < T; ++ti)
+                    for (int tj = ti; tj < T; ++tj) w[k++] = make_int4(b, ti, tj, 0);
+            }
+            VPK_CUDA(cudaMemcpyAsync(ctx->d_work.p, w, items * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+            {
+                KernelScope ks(ctx, "sphere_votes");
+                sphere_votes_kernel<<<(unsigned)items, kVoteThreads, 0, ctx->stream>>>(
+                    d_lines, d_offsets, ctx->d_work.as<int4>(), S, d_weights, d_hist, d_whist);
+                VPK_TRY(check_launch("sphere_votes"));
+            }
+            // the pinned work list must not be rewritten before the copy has run
+            VPK_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        return VPK_OK;
+    }
+    if (mode == VPK_SPHERE_CURVES) {
+        // column -> first sample index table, exactly as numpy.linspace + the bin map
+        VPK_TRY(ctx->h_stage.ensure((S + 1) * sizeof(int32_t) + kLutMax + 1));
+        int32_t* first = ctx->h_stage.as<int32_t>();
+        uint8_t* lut = reinterpret_cast<uint8_t*>(first + S + 1);
+        {
+            const double start = -0.5 * kPi, stop = 0.5 * kPi;
+            volatile double step = (stop - start) / (double)(kNumSamples - 1);
+            int c = 0;
+            first[0] = 0;
+            for (int k = 0; k < kNumSamples; ++k) {
+                volatile double a = (double)k * step;
+                a = a + start;
+                if (k == kNumSamples - 1) a = stop;
+                int col = host_angle_bin(a, S);
+                while (c < col) first[++c] = k;
+            }
+            while (c < S) first[++c] = kNumSamples;
+            for (int k = 0; k <= kLutMax; ++k)
+                lut[k] = (uint8_t)floor(255.0 * (1.0 - pow(1.0 - alpha, (double)k)));
+        }
+        size_t tab_bytes = (S + 1) * sizeof(int32_t) + kLutMax + 1;
+        size_t diff_bytes = sizeof(int32_t) * (size_t)(S + 1) * S * B;
+        VPK_TRY(ctx->d_work.ensure(tab_bytes));
+        VPK_TRY(ctx->d_misc.ensure(diff_bytes));
+        VPK_CUDA(cudaMemcpyAsync(ctx->d_work.p, first, tab_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        VPK_CUDA(cudaMemsetAsync(ctx->d_misc.p, 0, diff_bytes, ctx->stream));
+        const int32_t* d_first = ctx->d_work.as<int32_t>();
+        const uint8_t* d_lut = reinterpret_cast<const uint8_t*>(d_first + S + 1);
+        if (sumN > 0) {
+            KernelScope ks(ctx, "sphere_curves");
+            int threads = S >= 512 ? 512 : ((S + 31) / 32) * 32;
+            sphere_curves_kernel<<<(unsigned)sumN, threads, 0, ctx->stream>>>(d_lines, d_offsets, B, S, d_first, 1.0,
+                                                                               ctx->d_misc.as<int32_t>());
+            VPK_TRY(check_launch("sphere_curves"));
+        }
+        {
+            KernelScope ks(ctx, "curves_scan");
+            int64_t t = (int64_t)B * S;
+            curves_scan_kernel<<<(unsigned)((t + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_misc.as<int32_t>(), B, S, d_lut,
+                                                                                    d_hist, d_img);
+            VPK_TRY(check_launch("curves_scan"));
+        }
+        VPK_CUDA(cudaStreamSynchronize(ctx->stream));
+        return VPK_OK;
+    }
+    set_error("sphere_map: unknown mode %d", mode);
+    return VPK_ERR_ARG;
+}
+
+// votes -> uint8 image (and optional float export of the Q.16 sums)
+int sphere_votes_finish_dev(vpk_ctx* ctx, int32_t B, int32_t S, const uint32_t* d_hist,
+                            const unsigned long long* d_whist, uint8_t* d_img, float* d_wout) {
+    const int64_t plane = (int64_t)S * S;
+    VPK_TRY(ctx->d_weights.ensure(sizeof(unsigned long long) * (size_t)B));
+    unsigned long long* d_max = ctx->d_weights.as<unsigned long long>();
+    VPK_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned long long) * B, ctx->stream));
+    int64_t gx = (plane + 1023) / 1024;
+    dim3 grid((unsigned)(gx < 64 ? gx : 64), (unsigned)B);
+    {
+        KernelScope ks(ctx, "plane_max");
+        if (d_whist) plane_max_kernel<unsigned long long><<<grid, 256, 0, ctx->stream>>>(d_whist, plane, d_max);
+        else plane_max_kernel<uint32_t><<<grid, 256, 0, ctx->stream>>>(d_hist, plane, d_max);
+        VPK_TRY(check_launch("plane_max"));
+    }
+    if (d_img || d_wout) {
+        KernelScope ks(ctx, "votes_image");
+        if (d_whist) votes_image_kernel<unsigned long long><<<grid, 256, 0, ctx->stream>>>(d_whist, plane, d_max, d_img, d_wout);
+        else votes_image_kernel<uint32_t><<<grid, 256, 0, ctx->stream>>>(d_hist, plane, d_max, d_img, nullptr);
+        VPK_TRY(check_launch("votes_image"));
+    }
+    return VPK_OK;
+}
+
+}  // namespace vpk
+
+using namespace vpk;
+
+extern "C" {
+
+int vpk_lines_from_segments(vpk_ctx* ctx, const double* segments, int64_t n, double* lines_out) {
+    if (!ctx || (n > 0 && (!segments || !lines_out)) || n < 0) { set_error("vpk_lines_from_segments: bad argument"); return VPK_ERR_ARG; }
+    if (n == 0) return VPK_OK;
+    VPK_CUDA(cudaSetDevice(ctx->device));
+    VPK_TRY(ctx->d_segments.ensure(n * 4 * sizeof(double)));
+    VPK_TRY(ctx->d_lines.ensure(n * 3 * sizeof(double)));
+    VPK_CUDA(cudaMemcpyAsync(ctx->d_segments.p, segments, n * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    VPK_TRY(lines_from_segments_dev(ctx, ctx->d_segments.as<double>(), n, ctx->d_lines.as<double>()));
+    VPK_CUDA(cudaMemcpyAsync(lines_out, ctx->d_lines.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    VPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VPK_OK;
+}
+
+int vpk_sphere_map(vpk_ctx* ctx, const double* lines, const int32_t* offsets, int32_t B, int32_t S, int32_t mode,
+                   double alpha, const double* weights, uint32_t* hist_out, float* whist_out, uint8_t* image_out) {
+    if (!ctx || !offsets || B < 0 || S <= 0 || S > 4096) { set_error("vpk_sphere_map: bad argument"); return VPK_ERR_ARG; }
+    if (B == 0) return VPK_OK;
+    for (int b = 0; b < B; ++b)
+        if (offsets[b + 1] < offsets[b] || offsets[0] != 0) { set_error("vpk_sphere_map: offsets must start at 0 and be non-decreasing"); return VPK_ERR_ARG; }
+    const int64_t sumN = offsets[B];
+    if (sumN > 0 && !lines) { set_error("vpk_sphere_map: lines is NULL"); return VPK_ERR_ARG; }
+    if (mode == VPK_SPHERE_CURVES && weights) { set_error("vpk_sphere_map: weights apply to the votes mode only"); return VPK_ERR_ARG; }
+    const bool weighted = weights != nullptr;
+    if (hist_out && weighted) { set_error("vpk_sphere_map: hist_out is the unweighted output; use whist_out with weights"); return VPK_ERR_ARG; }
+    if (whist_out && !weighted) { set_error("vpk_sphere_map: whist_out needs weights"); return VPK_ERR_ARG; }
+    VPK_CUDA(cudaSetDevice(ctx->device));
+    const int64_t plane = (int64_t)S * S;
+    const size_t img_bytes = ((size_t)(plane * B + 15) / 16) * 16;
+    VPK_TRY(ctx->d_lines.ensure((sumN + 1) * 3 * sizeof(double)));
+    VPK_TRY(ctx->d_offsets.ensure((B + 1) * sizeof(int32_t)));
+    VPK_TRY(ctx->d_hist.ensure((weighted ? sizeof(unsigned long long) : sizeof(uint32_t)) * plane * B));
+    VPK_TRY(ctx->d_img.ensure(img_bytes + (whist_out ? sizeof(float) * plane * B : 0)));
+    if (sumN) VPK_CUDA(cudaMemcpyAsync(ctx->d_lines.p, lines, sumN * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    VPK_CUDA(cudaMemcpyAsync(ctx->d_offsets.p, offsets, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    double* d_w = nullptr;
+    if (weighted) {
+        VPK_TRY(ctx->d_segments.ensure((sumN + 1) * sizeof(double)));
+        d_w = ctx->d_segments.as<double>();
+        VPK_CUDA(cudaMemcpyAsync(d_w, weights, sumN * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    uint32_t* d_hist = weighted ? nullptr : ctx->d_hist.as<uint32_t>();
+    unsigned long long* d_whist = weighted ? ctx->d_hist.as<unsigned long long>() : nullptr;
+    uint8_t* d_img = ctx->d_img.as<uint8_t>();
+    float* d_wout = whist_out ? reinterpret_cast<float*>(d_img + img_bytes) : nullptr;
+    VPK_TRY(sphere_map_dev(ctx, ctx->d_lines.as<double>(), ctx->d_offsets.as<int32_t>(), offsets, B, S, mode, alpha, d_w,
+                           d_hist, d_whist, d_img));
+    if (mode == VPK_SPHERE_VOTES && (image_out || whist_out))
+        VPK_TRY(sphere_votes_finish_dev(ctx, B, S, d_hist, d_whist, image_out ? d_img : nullptr, d_wout));
+    if (hist_out) VPK_CUDA(cudaMemcpyAsync(hist_out, d_hist, sizeof(uint32_t) * plane * B, cudaMemcpyDeviceToHost, ctx->stream));
+    if (whist_out) VPK_CUDA(cudaMemcpyAsync(whist_out, d_wout, sizeof(float) * plane * B, cudaMemcpyDeviceToHost, ctx->stream));
+    if (image_out) VPK_CUDA(cudaMemcpyAsync(image_out, d_img, plane * B, cudaMemcpyDeviceToHost, ctx->stream));
+    VPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VPK_OK;
+}
+
+}  // extern "C"
