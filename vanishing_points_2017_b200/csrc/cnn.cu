@@ -1,6 +1,465 @@
+// Stage 2: forward pass of cnn/deploy.prototxt (reference evaluation.py:17-38).
+//
+// data 1x500x500 -> conv1(96,k11,s4)+ReLU -> LRN -> pool -> conv2(256,k5,p2,g2)
+// +ReLU -> LRN -> pool -> conv3(384,k3,p1)+ReLU -> conv4(384,k3,p1,g2)+ReLU ->
+// conv5(256,k3,p1,g2)+ReLU -> pool -> fc6+ReLU -> fc7+ReLU -> fc8 -> sigmoid.
+//
+// Every contraction runs on the tcgen05 implicit-GEMM kernel of
+// gemm_tcgen05.cuh; activations are bf16 NHWC with the next layer's zero
+// padding stored in memory, so a k x k convolution is k*k row-shifted 2-D TMA
+// loads of the same tensor.  conv1 (stride 4, one input channel) is first
+// turned into a stride-1 3x3 convolution over a 4x4 space-to-depth image.
+// Bias + ReLU are fused into the GEMM epilogue; LRN + max-pool are one fused
+// elementwise kernel (Caffe semantics: ACROSS_CHANNELS, ceil-mode pooling).
+#include <math.h>
 #include "vpk_internal.cuh"
-namespace vpk { void cnn_free(vpk_ctx*) {} }
-extern "C" {
-int vpk_cnn_load(vpk_ctx*, const float* const*, const float* const*, const float*) { vpk::set_error("vpk_cnn_load: not built yet"); return VPK_ERR_STATE; }
-int vpk_cnn_forward(vpk_ctx*, const uint8_t*, int32_t, float*, float*) { vpk::set_error("vpk_cnn_forward: not built yet"); return VPK_ERR_STATE; }
+#include "gemm_tcgen05.cuh"
+
+namespace vpk {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct CnnState {
+    bool loaded = false;
+    EncodeTiledFn encode = nullptr;
+    // bf16 weight matrices (K-major) and fp32 biases, one per layer conv1..fc8
+    DBuf w[8], b[8], mean;
+    bool has_mean = false;
+    // activations (sized for `cap` images)
+    int cap = 0;
+    DBuf a1, c1, a2, c2, a3, a4, a5, c5, a6, f6, f7, logits, sig, img;
+};
+
+void cnn_free(vpk_ctx* ctx) {
+    if (!ctx->cnn) return;
+    CnnState* s = ctx->cnn;
+    for (int i = 0; i < 8; ++i) { s->w[i].release(); s->b[i].release(); }
+    s->mean.release();
+    DBuf* bufs[] = {&s->a1, &s->c1, &s->a2, &s->c2, &s->a3, &s->a4, &s->a5, &s->c5, &s->a6, &s->f6, &s->f7, &s->logits, &s->sig, &s->img};
+    for (DBuf* d : bufs) d->release();
+    delete s;
+    ctx->cnn = nullptr;
 }
+
+// ---------------------------------------------------------------------------
+// weight repacking (device side): fp32 Caffe blobs -> bf16 K-major GEMM operands
+// ---------------------------------------------------------------------------
+enum { PACK_CONV1 = 0, PACK_CONV = 1, PACK_FC6 = 2, PACK_PLAIN = 3 };
+
+// dst[o, k] for o < n_out, k < k_total
+__global__ void pack_weights_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int mode, int n_out,
+                                    long long k_total, int cin_g, int cpad, int ksz) {
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_out * k_total) return;
+    int o = (int)(idx / k_total);
+    long long k = idx % k_total;
+    float v = 0.f;
+    if (mode == PACK_CONV1) {
+        // k = khb*64 + kwb*16 + dy*4 + dx  ->  W[o][0][4*khb+dy][4*kwb+dx]   (11x11, zero beyond)
+        int khb = (int)(k / 64), r = (int)(k % 64), kwb = r / 16, dy = (r % 16) / 4, dx = r % 4;
+        int row = 4 * khb + dy, col = 4 * kwb + dx;
+        if (row < 11 && col < 11) v = src[(o * 11 + row) * 11 + col];
+    } else if (mode == PACK_CONV) {
+        // k = tap*cpad + c  ->  W[o][c][kh][kw]  (c < cin_g, zero for the channel padding)
+        int tap = (int)(k / cpad), c = (int)(k % cpad);
+        if (c < cin_g) v = src[((long long)o * cin_g + c) * ksz * ksz + tap];
+    } else if (mode == PACK_FC6) {
+        // ours: k = (y*15+x)*256 + c ; Caffe flattens NCHW: c*225 + y*15 + x
+        int pix = (int)(k / 256), c = (int)(k % 256);
+        v = src[(long long)o * k_total + (long long)c * 225 + pix];
+    } else {
+        v = src[(long long)o * k_total + k];
+    }
+    dst[idx] = __float2bfloat16_rn(v);
+}
+
+// ---------------------------------------------------------------------------
+// elementwise kernels
+// ---------------------------------------------------------------------------
+// image - mean -> conv1 operand: row (n, Y, X) of the 125x125 block grid holds the
+// 4x4 pixel blocks X..X+3 of block row Y (64 bf16), so the three kernel block rows
+// are three row-shifted K blocks of one 2-D tensor.
+__global__ void conv1_operand_kernel(const uint8_t* __restrict__ img, const float* __restrict__ mean, int n_images,
+                                     __nv_bfloat16* __restrict__ a1) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;      // one thread per (row, 8-value chunk)
+    long long rows = (long long)n_images * 15625;
+    if (t >= rows * 8) return;
+    long long m = t >> 3;
+    int q = (int)(t & 7);
+    int n = (int)(m / 15625), r = (int)(m % 15625), Y = r / 125, X = r % 125;
+    int kwb = q >> 1;
+    uint32_t pk[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        int dy = (q & 1) * 2 + h;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (X + kwb < 125) {
+            int py = 4 * Y + dy, px = 4 * (X + kwb);
+            const uint8_t* p = img + ((long long)n * 500 + py) * 500 + px;
+            uchar4 u = *reinterpret_cast<const uchar4*>(p);
+            v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
+            if (mean) {
+                const float* mp = mean + py * 500 + px;
+                v[0] -= mp[0]; v[1] -= mp[1]; v[2] -= mp[2]; v[3] -= mp[3];
+            }
+        }
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+        pk[2 * h] = *reinterpret_cast<uint32_t*>(&lo);
+        pk[2 * h + 1] = *reinterpret_cast<uint32_t*>(&hi);
+    }
+    *reinterpret_cast<uint4*>(a1 + m * 64 + q * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
+// Fused LRN (ACROSS_CHANNELS, size 5, alpha 1e-4, beta 0.75, k 1) + 3x3/2 ceil-mode max
+// pool (Caffe).  in: NHWC (n,H,W,C) bf16.  out: (n, Ho+2*opad, Wo+2*opad, Cout) with
+// channel c stored at (c / cg) * cgp + c % cg  (group padding of the next convolution).
+__global__ void lrn_pool_kernel(const __nv_bfloat16* __restrict__ in, int n_images, int H, int W, int C, int do_lrn,
+                                int Ho, int Wo, int opad, int Cout, int cg, int cgp, __nv_bfloat16* __restrict__ out) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long total = (long long)n_images * Ho * Wo * C;
+    if (t >= total) return;
+    int c = (int)(t % C);
+    long long r = t / C;
+    int ox = (int)(r % Wo); r /= Wo;
+    int oy = (int)(r % Ho);
+    int n = (int)(r / Ho);
+    int y0 = oy * 2, x0 = ox * 2, y1 = min(y0 + 3, H), x1 = min(x0 + 3, W);
+    float best = -INFINITY;
+    for (int y = y0; y < y1; ++y)
+        for (int x = x0; x < x1; ++x) {
+            const __nv_bfloat16* p = in + (((long long)n * H + y) * W + x) * C;
+            float v = __bfloat162float(p[c]);
+            if (do_lrn) {
+                float ss = 0.f;
+#pragma unroll
+                for (int d = -2; d <= 2; ++d) {
+                    int cc = c + d;
+                    if (cc >= 0 && cc < C) { float u = __bfloat162float(p[cc]); ss += u * u; }
+                }
+                v = v * __powf(1.f + (1e-4f / 5.f) * ss, -0.75f);
+            }
+            best = fmaxf(best, v);
+        }
+    int Hop = Ho + 2 * opad, Wop = Wo + 2 * opad;
+    int co = (c / cg) * cgp + (c % cg);
+    out[(((long long)n * Hop + oy + opad) * Wop + ox + opad) * Cout + co] = __float2bfloat16_rn(best);
+}
+
+__global__ void sigmoid_kernel(const float* __restrict__ x, long long n, float* __restrict__ y) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) y[i] = 1.f / (1.f + __expf(-x[i]));
+}
+
+// ---------------------------------------------------------------------------
+// GEMM launch
+// ---------------------------------------------------------------------------
+static int make_map(CnnState* st, CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t pitch_bytes,
+                    uint32_t box_rows) {
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t strides[1] = {pitch_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = st->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): inner=%llu rows=%llu pitch=%llu box_rows=%u", (int)r,
+                  (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)pitch_bytes, box_rows);
+        return VPK_ERR_CUDA;
+    }
+    return VPK_OK;
+}
+
+struct GemmCall {
+    const char* name;
+    const void* A; uint64_t a_inner, a_rows, a_pitch;     // A tensor: inner elements, rows, pitch bytes
+    const void* B; uint64_t b_inner, b_rows;              // B tensor (pitch = inner*2)
+    int groups;
+    GemmParams p;
+};
+
+int launch_gemm(vpk_ctx* ctx, const GemmCall& c) {
+    CnnState* st = ctx->cnn;
+    CUtensorMap ma, mb;
+    VPK_TRY(make_map(st, &ma, c.A, c.a_inner, c.a_rows, c.a_pitch, kBM));
+    VPK_TRY(make_map(st, &mb, c.B, c.b_inner, c.b_rows, c.b_inner * 2, (uint32_t)c.p.bn));
+    const int m_tiles = (c.p.m_total + kBM - 1) / kBM;
+    const int n_tiles = (c.p.n_valid + c.p.bn - 1) / c.p.bn;
+    dim3 grid(m_tiles, n_tiles, c.groups);
+    const size_t stage = kABytes + (size_t)c.p.bn * kBK * 2;
+    KernelScope ks(ctx, c.name);
+    if (c.p.bn <= 128) {
+        size_t smem = 3 * stage + 1024;
+        static bool attr3 = false;
+        if (!attr3) { VPK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (kABytes + 128 * kBK * 2) + 1024)); attr3 = true; }
+        gemm_bf16_tcgen05_kernel<3><<<grid, kGemmThreads, smem, ctx->stream>>>(ma, mb, c.p);
+    } else {
+        size_t smem = 4 * stage + 1024;
+        static bool attr4 = false;
+        if (!attr4) { VPK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (kABytes + 256 * kBK * 2) + 1024)); attr4 = true; }
+        gemm_bf16_tcgen05_kernel<4><<<grid, kGemmThreads, smem, ctx->stream>>>(ma, mb, c.p);
+    }
+    return check_launch(c.name);
+}
+
+static GemmParams plain_params(int m, int n, int k, int bn, int ldc, const float* bias, int relu, int out_f32, void* out) {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.m_total = m; p.k_blocks = k / kBK; p.cblocks = k / kBK; p.taps_x = 1; p.row_pitch = 0;
+    p.hp_wp = 1; p.wp = 1; p.h_valid = 1; p.w_valid = 1; p.out_hp_wp = 1; p.out_wp = 1; p.out_pad = 0;
+    p.ldc = ldc; p.n_valid = n; p.relu = relu; p.out_f32 = out_f32; p.bn = bn; p.bias = bias; p.out = out;
+    return p;
+}
+
+static int ensure_driver_entry(CnnState* st) {
+    if (st->encode) return VPK_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver (%s)", cudaGetErrorString(e));
+        return VPK_ERR_CUDA;
+    }
+    st->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return VPK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------
+static int ensure_activations(vpk_ctx* ctx, int n) {
+    CnnState* s = ctx->cnn;
+    if (n <= s->cap) return VPK_OK;
+    size_t N = (size_t)n;
+    struct { DBuf* d; size_t bytes; bool zero; } plan[] = {
+        {&s->a1, N * 15625 * 64 * 2 + 256, false},            // conv1 operand (125x125 rows x 64)
+        {&s->c1, N * 123 * 123 * 96 * 2, false},              // conv1 out
+        {&s->a2, N * 65 * 65 * 128 * 2, true},                // conv2 in: pad 2, 2 groups x (48 -> 64)
+        {&s->c2, N * 61 * 61 * 256 * 2, false},               // conv2 out
+        {&s->a3, N * 32 * 32 * 256 * 2, true},                // conv3 in: pad 1
+        {&s->a4, N * 32 * 32 * 384 * 2, true},                // conv4 in: pad 1
+        {&s->a5, N * 32 * 32 * 384 * 2, true},                // conv5 in: pad 1
+        {&s->c5, N * 30 * 30 * 256 * 2, false},               // conv5 out
+        {&s->a6, N * 57600 * 2, false},                       // pool5 = fc6 in
+        {&s->f6, N * 4096 * 2, false},
+        {&s->f7, N * 4096 * 2, false},
+        {&s->logits, N * 400 * 4, false},
+        {&s->sig, N * 400 * 4, false},
+    };
+    for (auto& e : plan) {
+        VPK_TRY(e.d->ensure(e.bytes));
+        if (e.zero) VPK_CUDA(cudaMemsetAsync(e.d->p, 0, e.d->cap, ctx->stream));
+    }
+    s->cap = n;
+    return VPK_OK;
+}
+
+int cnn_forward_dev(vpk_ctx* ctx, const uint8_t* d_images, int32_t n, float* d_sigout, float* d_logits) {
+    CnnState* s = ctx->cnn;
+    if (!s || !s->loaded) { set_error("vpk_cnn_forward: call vpk_cnn_load first"); return VPK_ERR_STATE; }
+    if (n <= 0) return VPK_OK;
+    VPK_TRY(ensure_activations(ctx, n));
+    typedef __nv_bfloat16 bf;
+    const float* mean = s->has_mean ? s->mean.as<float>() : nullptr;
+    {
+        KernelScope ks(ctx, "conv1_operand");
+        long long t = (long long)n * 15625 * 8;
+        conv1_operand_kernel<<<(unsigned)((t + 255) / 256), 256, 0, ctx->stream>>>(d_images, mean, n, s->a1.as<bf>());
+        VPK_TRY(check_launch("conv1_operand"));
+    }
+    GemmCall c;
+    // conv1: 3 block rows x 64 (4 blocks x 16) -> 96
+    memset(&c, 0, sizeof(c));
+    c.name = "gemm_conv1"; c.A = s->a1.p; c.a_inner = 64; c.a_rows = (uint64_t)n * 15625; c.a_pitch = 128;
+    c.B = s->w[0].p; c.b_inner = 192; c.b_rows = 96; c.groups = 1;
+    c.p.m_total = n * 15625; c.p.k_blocks = 3; c.p.cblocks = 1; c.p.taps_x = 1; c.p.row_pitch = 125;
+    c.p.hp_wp = 15625; c.p.wp = 125; c.p.h_valid = 123; c.p.w_valid = 123;
+    c.p.out_hp_wp = 123 * 123; c.p.out_wp = 123; c.p.out_pad = 0; c.p.ldc = 96; c.p.n_valid = 96; c.p.relu = 1; c.p.bn = 96;
+    c.p.bias = s->b[0].as<float>(); c.p.out = s->c1.p;
+    VPK_TRY(launch_gemm(ctx, c));
+    {
+        KernelScope ks(ctx, "lrn_pool1");
+        long long t = (long long)n * 61 * 61 * 96;
+        lrn_pool_kernel<<<(unsigned)((t + 255) / 256), 256, 0, ctx->stream>>>(s->c1.as<bf>(), n, 123, 123, 96, 1, 61, 61, 2, 128, 48, 64, s->a2.as<bf>());
+        VPK_TRY(check_launch("lrn_pool1"));
+    }
+    // conv2: 5x5 pad 2, 2 groups of 48 (stored as 64) -> 128 each
+    memset(&c, 0, sizeof(c));
+    c.name = "gemm_conv2"; c.A = s->a2.p; c.a_inner = 128; c.a_rows = (uint64_t)n * 4225; c.a_pitch = 256;
+    c.B = s->w[1].p; c.b_inner = 1600; c.b_rows = 256; c.groups = 2;
+    c.p.m_total = n * 4225; c.p.k_blocks = 25; c.p.cblocks = 1; c.p.taps_x = 5; c.p.row_pitch = 65; c.p.a_col_group = 64; c.p.b_row_group = 128;
+    c.p.hp_wp = 4225; c.p.wp = 65; c.p.h_valid = 61; c.p.w_valid = 61;
+    c.p.out_hp_wp = 61 * 61; c.p.out_wp = 61; c.p.out_pad = 0; c.p.ldc = 256; c.p.c_col_group = 128; c.p.n_valid = 128; c.p.relu = 1; c.p.bn = 128;
+    c.p.bias = s->b[1].as<float>(); c.p.out = s->c2.p;
+    VPK_TRY(launch_gemm(ctx, c));
+    {
+        KernelScope ks(ctx, "lrn_pool2");
+        long long t = (long long)n * 30 * 30 * 256;
+        lrn_pool_kernel<<<(unsigned)((t + 255) / 256), 256, 0, ctx->stream>>>(s->c2.as<bf>(), n, 61, 61, 256, 1, 30, 30, 1, 256, 256, 256, s->a3.as<bf>());
+        VPK_TRY(check_launch("lrn_pool2"));
+    }
+    // conv3: 3x3 pad 1, 256 -> 384, written into conv4's padded input
+    memset(&c, 0, sizeof(c));
+    c.name = "gemm_conv3"; c.A = s->a3.p; c.a_inner = 256; c.a_rows = (uint64_t)n * 1024; c.a_pitch = 512;
+    c.B = s->w[2].p; c.b_inner = 2304; c.b_rows = 384; c.groups = 1;
+    c.p.m_total = n * 1024; c.p.k_blocks = 36; c.p.cblocks = 4; c.p.taps_x = 3; c.p.row_pitch = 32;
+    c.p.hp_wp = 1024; c.p.wp = 32; c.p.h_valid = 30; c.p.w_valid = 30;
+    c.p.out_hp_wp = 1024; c.p.out_wp = 32; c.p.out_pad = 1; c.p.ldc = 384; c.p.n_valid = 384; c.p.relu = 1; c.p.bn = 128;
+    c.p.bias = s->b[2].as<float>(); c.p.out = s->a4.p;
+    VPK_TRY(launch_gemm(ctx, c));
+    // conv4: 3x3 pad 1, 2 groups 192 -> 192, into conv5's padded input
+    memset(&c, 0, sizeof(c));
+    c.name = "gemm_conv4"; c.A = s->a4.p; c.a_inner = 384; c.a_rows = (uint64_t)n * 1024; c.a_pitch = 768;
+    c.B = s->w[3].p; c.b_inner = 1728; c.b_rows = 384; c.groups = 2;
+    c.p.m_total = n * 1024; c.p.k_blocks = 27; c.p.cblocks = 3; c.p.taps_x = 3; c.p.row_pitch = 32; c.p.a_col_group = 192; c.p.b_row_group = 192;
+    c.p.hp_wp = 1024; c.p.wp = 32; c.p.h_valid = 30; c.p.w_valid = 30;
+    c.p.out_hp_wp = 1024; c.p.out_wp = 32; c.p.out_pad = 1; c.p.ldc = 384; c.p.c_col_group = 192; c.p.n_valid = 192; c.p.relu = 1; c.p.bn = 192;
+    c.p.bias = s->b[3].as<float>(); c.p.out = s->a5.p;
+    VPK_TRY(launch_gemm(ctx, c));
+    // conv5: 3x3 pad 1, 2 groups 192 -> 128
+    memset(&c, 0, sizeof(c));
+    c.name = "gemm_conv5"; c.A = s->a5.p; c.a_inner = 384; c.a_rows = (uint64_t)n * 1024; c.a_pitch = 768;
+    c.B = s->w[4].p; c.b_inner = 1728; c.b_rows = 256; c.groups = 2;
+    c.p.m_total = n * 1024; c.p.k_blocks = 27; c.p.cblocks = 3; c.p.taps_x = 3; c.p.row_pitch = 32; c.p.a_col_group = 192; c.p.b_row_group = 128;
+    c.p.hp_wp = 1024; c.p.wp = 32; c.p.h_valid = 30; c.p.w_valid = 30;
+    c.p.out_hp_wp = 900; c.p.out_wp = 30; c.p.out_pad = 0; c.p.ldc = 256; c.p.c_col_group = 128; c.p.n_valid = 128; c.p.relu = 1; c.p.bn = 128;
+    c.p.bias = s->b[4].as<float>(); c.p.out = s->c5.p;
+    VPK_TRY(launch_gemm(ctx, c));
+    {
+        KernelScope ks(ctx, "pool5");
+        long long t = (long long)n * 15 * 15 * 256;
+        lrn_pool_kernel<<<(unsigned)((t + 255) / 256), 256, 0, ctx->stream>>>(s->c5.as<bf>(), n, 30, 30, 256, 0, 15, 15, 0, 256, 256, 256, s->a6.as<bf>());
+        VPK_TRY(check_launch("pool5"));
+    }
+    // fc6 / fc7 / fc8
+    memset(&c, 0, sizeof(c));
+    c.name = "gemm_fc6"; c.A = s->a6.p; c.a_inner = 57600; c.a_rows = n; c.a_pitch = 57600 * 2;
+    c.B = s->w[5].p; c.b_inner = 57600; c.b_rows = 4096; c.groups = 1;
+    c.p = plain_params(n, 4096, 57600, 256, 4096, s->b[5].as<float>(), 1, 0, s->f6.p);
+    VPK_TRY(launch_gemm(ctx, c));
+    c.name = "gemm_fc7"; c.A = s->f6.p; c.a_inner = 4096; c.a_rows = n; c.a_pitch = 8192;
+    c.B = s->w[6].p; c.b_inner = 4096; c.b_rows = 4096;
+    c.p = plain_params(n, 4096, 4096, 256, 4096, s->b[6].as<float>(), 1, 0, s->f7.p);
+    VPK_TRY(launch_gemm(ctx, c));
+    float* logits = d_logits ? d_logits : s->logits.as<float>();
+    c.name = "gemm_fc8"; c.A = s->f7.p; c.a_inner = 4096; c.a_rows = n; c.a_pitch = 8192;
+    c.B = s->w[7].p; c.b_inner = 4096; c.b_rows = 400;
+    c.p = plain_params(n, 400, 4096, 80, 400, s->b[7].as<float>(), 0, 1, logits);
+    VPK_TRY(launch_gemm(ctx, c));
+    if (d_sigout) {
+        KernelScope ks(ctx, "sigmoid");
+        long long t = (long long)n * 400;
+        sigmoid_kernel<<<(unsigned)((t + 255) / 256), 256, 0, ctx->stream>>>(logits, t, d_sigout);
+        VPK_TRY(check_launch("sigmoid"));
+    }
+    return VPK_OK;
+}
+
+}  // namespace vpk
+
+using namespace vpk;
+
+extern "C" {
+
+int vpk_cnn_load(vpk_ctx* ctx, const float* const* weights, const float* const* biases, const float* mean) {
+    if (!ctx || !weights || !biases) { set_error("vpk_cnn_load: bad argument"); return VPK_ERR_ARG; }
+    VPK_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->cnn) ctx->cnn = new CnnState();
+    CnnState* s = ctx->cnn;
+    VPK_TRY(ensure_driver_entry(s));
+    // (n_out, source elements, packed K, mode, cin_g, cpad, ksz)
+    struct L { int n_out; long long src; long long k; int mode, cin_g, cpad, ksz; };
+    const L layers[8] = {
+        {96, 96LL * 121, 192, PACK_CONV1, 1, 0, 11},
+        {256, 256LL * 48 * 25, 1600, PACK_CONV, 48, 64, 5},
+        {384, 384LL * 256 * 9, 2304, PACK_CONV, 256, 256, 3},
+        {384, 384LL * 192 * 9, 1728, PACK_CONV, 192, 192, 3},
+        {256, 256LL * 192 * 9, 1728, PACK_CONV, 192, 192, 3},
+        {4096, 4096LL * 57600, 57600, PACK_FC6, 0, 0, 0},
+        {4096, 4096LL * 4096, 4096, PACK_PLAIN, 0, 0, 0},
+        {400, 400LL * 4096, 4096, PACK_PLAIN, 0, 0, 0},
+    };
+    for (int i = 0; i < 8; ++i) {
+        if (!weights[i] || !biases[i]) { set_error("vpk_cnn_load: layer %d weights/bias NULL", i); return VPK_ERR_ARG; }
+        const L& l = layers[i];
+        VPK_TRY(ctx->d_misc.ensure(l.src * sizeof(float)));
+        VPK_CUDA(cudaMemcpyAsync(ctx->d_misc.p, weights[i], l.src * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        VPK_TRY(s->w[i].ensure((size_t)l.n_out * l.k * 2));
+        VPK_TRY(s->b[i].ensure((size_t)l.n_out * sizeof(float)));
+        long long total = (long long)l.n_out * l.k;
+        {
+            KernelScope ks(ctx, "pack_weights");
+            pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
+                ctx->d_misc.as<float>(), s->w[i].as<__nv_bfloat16>(), l.mode, l.n_out, l.k, l.cin_g, l.cpad, l.ksz);
+            VPK_TRY(check_launch("pack_weights"));
+        }
+        VPK_CUDA(cudaMemcpyAsync(s->b[i].p, biases[i], (size_t)l.n_out * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        VPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    s->has_mean = mean != nullptr;
+    if (mean) {
+        VPK_TRY(s->mean.ensure(250000 * sizeof(float)));
+        VPK_CUDA(cudaMemcpyAsync(s->mean.p, mean, 250000 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        VPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    s->loaded = true;
+    return VPK_OK;
+}
+
+int vpk_cnn_forward(vpk_ctx* ctx, const uint8_t* images, int32_t n, float* sigout, float* logits_out) {
+    if (!ctx || n < 0 || (n > 0 && (!images || !sigout))) { set_error("vpk_cnn_forward: bad argument"); return VPK_ERR_ARG; }
+    if (n == 0) return VPK_OK;
+    VPK_CUDA(cudaSetDevice(ctx->device));
+    CnnState* s = ctx->cnn;
+    if (!s || !s->loaded) { set_error("vpk_cnn_forward: call vpk_cnn_load first"); return VPK_ERR_STATE; }
+    const int chunk = 1024;
+    for (int i0 = 0; i0 < n; i0 += chunk) {
+        int nb = n - i0 < chunk ? n - i0 : chunk;
+        VPK_TRY(ensure_activations(ctx, nb));
+        VPK_TRY(s->img.ensure((size_t)nb * 250000));
+        VPK_CUDA(cudaMemcpyAsync(s->img.p, images + (size_t)i0 * 250000, (size_t)nb * 250000, cudaMemcpyHostToDevice, ctx->stream));
+        VPK_TRY(cnn_forward_dev(ctx, s->img.as<uint8_t>(), nb, s->sig.as<float>(), nullptr));
+        VPK_CUDA(cudaMemcpyAsync(sigout + (size_t)i0 * 400, s->sig.p, (size_t)nb * 400 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        if (logits_out)
+            VPK_CUDA(cudaMemcpyAsync(logits_out + (size_t)i0 * 400, s->logits.p, (size_t)nb * 400 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        VPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return VPK_OK;
+}
+
+// Diagnostics: one plain GEMM through the tcgen05 kernel.  a (m,k), b (n,k) are
+// bf16 bit patterns (uint16), bias (n) float32 or NULL, out (m,n) float32.
+int vpk_debug_gemm(vpk_ctx* ctx, int32_t m, int32_t n, int32_t k, const uint16_t* a, const uint16_t* b, const float* bias,
+                   int32_t relu, int32_t bn, float* out) {
+    if (!ctx || !a || !b || !out || m <= 0 || n <= 0 || k <= 0 || k % 64 || bn % 16 || bn < 16 || bn > 256 || n % bn) {
+        set_error("vpk_debug_gemm: bad argument (k %% 64 == 0, bn %% 16 == 0, n %% bn == 0 required)");
+        return VPK_ERR_ARG;
+    }
+    VPK_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->cnn) ctx->cnn = new CnnState();
+    VPK_TRY(ensure_driver_entry(ctx->cnn));
+    DBuf da, db, dbias, dout;
+    int rc = VPK_OK;
+    do {
+        if ((rc = da.ensure((size_t)m * k * 2)) || (rc = db.ensure((size_t)n * k * 2)) || (rc = dout.ensure((size_t)m * n * 4)) ||
+            (rc = dbias.ensure((size_t)n * 4))) break;
+        cudaMemcpyAsync(da.p, a, (size_t)m * k * 2, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(db.p, b, (size_t)n * k * 2, cudaMemcpyHostToDevice, ctx->stream);
+        if (bias) cudaMemcpyAsync(dbias.p, bias, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
+        GemmCall c;
+        memset(&c, 0, sizeof(c));
+        c.name = "gemm_debug"; c.A = da.p; c.a_inner = k; c.a_rows = m; c.a_pitch = (uint64_t)k * 2;
+        c.B = db.p; c.b_inner = k; c.b_rows = n; c.groups = 1;
+        c.p = plain_params(m, n, k, bn, n, bias ? dbias.as<float>() : nullptr, relu, 1, dout.p);
+        if ((rc = launch_gemm(ctx, c))) break;
+        cudaMemcpyAsync(out, dout.p, (size_t)m * n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { set_error("vpk_debug_gemm: %s", cudaGetErrorString(e)); rc = VPK_ERR_CUDA; }
+    } while (0);
+    da.release(); db.release(); dbias.release(); dout.release();
+    return rc;
+}
+
+}  // extern "C"

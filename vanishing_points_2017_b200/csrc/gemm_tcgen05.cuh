@@ -1,0 +1,243 @@
+// bf16 x bf16 -> fp32 GEMM for sm_100a: TMA-fed, tcgen05.mma with the
+// accumulator in tensor memory, warp-specialised (TMA producer / MMA issuer /
+// 4 epilogue warps), used for every dense contraction of cnn/deploy.prototxt.
+//
+//   D[m, n] = act( sum_k A[row(m, k), k] * B[n, k] + bias[n] )
+//
+// A and B are K-major (K contiguous).  A convolution is run as an *implicit*
+// GEMM without materialising im2col: the activation tensor is stored NHWC with
+// its zero padding in memory, the output rows m enumerate the PADDED grid
+// (n, y, x) of the input, and kernel tap (kh, kw) of output row m is input row
+// m + kh*Wp + kw -- a plain row shift of the 2-D TMA box.  Output rows that fall
+// into the padding (x >= W or y >= H) are computed and dropped in the epilogue.
+//
+// Shared-memory operand tiles use the 128-byte swizzle written by TMA
+// (CU_TENSOR_MAP_SWIZZLE_128B) and read by the UMMA descriptors below
+// (layout_type 2, SBO = 1024 B); the K-slice of one tcgen05.mma (16 bf16 = 32 B)
+// is selected by advancing the descriptor start address.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vpk {
+
+static constexpr int kGemmThreads = 192;       // warp0 TMA, warp1 MMA/TMEM, warps 2-5 epilogue
+static constexpr int kBM = 128;                // UMMA_M (cta_group::1)
+static constexpr int kBK = 64;                 // bf16 per 128-byte swizzle row
+static constexpr int kABytes = kBM * kBK * 2;  // 16 KiB per stage
+
+struct GemmParams {
+    // ---- operand addressing
+    int m_total;       // rows of the (padded) output grid
+    int k_blocks;      // number of 64-wide K blocks
+    int cblocks;       // K blocks per kernel tap (channels/64)
+    int taps_x;        // taps per kernel row (1 for plain GEMM)
+    int row_pitch;     // Wp: A row shift per kernel row
+    int a_col_group;   // A column offset per group
+    int b_row_group;   // B row offset per group
+    // ---- epilogue
+    int hp_wp, wp, h_valid, w_valid;       // m -> (n, y, x); valid if y < h_valid and x < w_valid
+    int out_hp_wp, out_wp, out_pad;        // output row = n*out_hp_wp + (y+out_pad)*out_wp + (x+out_pad)
+    int ldc;                               // output row pitch (elements)
+    int c_col_group;                       // output column offset per group
+    int n_valid;                           // output columns per group
+    int relu, out_f32;
+    int bn;                                // N tile (multiple of 16, <= 256)
+    const float* bias;                     // [groups * n_valid] or nullptr
+    void* out;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t i = 0; i < (1u << 22); ++i)
+        if (mbar_try_wait(bar, parity)) return;
+    __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, 128-byte swizzle operand descriptor (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);        // start address  [0,14)
+    d |= (uint64_t)1 << 16;                        // LBO (unused for swizzled K-major) [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;              // SBO = 8 rows * 128 B  [32,46)
+    d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M x N
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int kStages>
+__global__ void __launch_bounds__(kGemmThreads)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[kStages], bar_empty[kStages], bar_acc;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_bytes = (uint32_t)p.bn * kBK * 2;
+    const uint32_t sA = sbase, sB = sbase + kStages * kABytes;
+    const int m0 = blockIdx.x * kBM;
+    const int n0 = blockIdx.y * p.bn;
+    const int g = blockIdx.z;
+    uint32_t ncols = 32;
+    while ((int)ncols < p.bn) ncols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        mbar_init(smem_u32(&bar_acc), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            for (int kb = 0; kb < p.k_blocks; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+                mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+                const uint32_t full = smem_u32(&bar_full[s]);
+                mbar_expect_tx(full, kABytes + b_bytes);
+                const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+                const int kh = tap / p.taps_x, kw = tap - kh * p.taps_x;
+                tma_load_2d(sA + s * kABytes, &tmA, full, g * p.a_col_group + cb * kBK, m0 + kh * p.row_pitch + kw);
+                tma_load_2d(sB + s * b_bytes, &tmB, full, kb * kBK, g * p.b_row_group + n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = umma_idesc_bf16(kBM, p.bn);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+            const int s = kb % kStages;
+            const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+            mbar_wait(smem_u32(&bar_full[s]), ph);
+            tcgen05_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+                    uint64_t ad = umma_desc_sw128(sA + s * kABytes + k * 32);
+                    uint64_t bd = umma_desc_sw128(sB + s * b_bytes + k * 32);
+                    tcgen05_mma_bf16(tmem, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                }
+                tcgen05_commit(smem_u32(&bar_empty[s]));        // frees the smem stage when the MMAs retire
+                if (kb == p.k_blocks - 1) tcgen05_commit(smem_u32(&bar_acc));
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> bias/ReLU -> global =====
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
+        const int row = quarter * 32 + lane;
+        const int m = m0 + row;
+        bool valid = m < p.m_total;
+        long long orow = 0;
+        if (valid) {
+            int n = m / p.hp_wp, r = m - n * p.hp_wp;
+            int y = r / p.wp, x = r - y * p.wp;
+            valid = (y < p.h_valid) && (x < p.w_valid);
+            orow = (long long)n * p.out_hp_wp + (long long)(y + p.out_pad) * p.out_wp + (x + p.out_pad);
+        }
+        mbar_wait(smem_u32(&bar_acc), 0);
+        tcgen05_fence_after();
+        const int ccol0 = g * p.c_col_group + n0;
+        for (int c = 0; c < p.bn; c += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
+            if (!valid || n0 + c >= p.n_valid) continue;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float x = __uint_as_float(r[j]);
+                if (p.bias) x += __ldg(p.bias + g * p.n_valid + n0 + c + j);
+                v[j] = p.relu ? fmaxf(x, 0.f) : x;
+            }
+            if (p.out_f32) {
+                float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldc + ccol0 + c);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                    pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldc + ccol0 + c);
+                o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols) : "memory");
+    }
+}
+
+}  // namespace vpk
