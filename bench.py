@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the lines->VPs hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C] [--impl ours|reference]
+
+One "step" = one pass of the path (segments -> lines -> sphere votes -> CNN ->
+EM -> VPs) over one synthetic batch of BASELINE.json config C (default 2: the
+YUD-shaped batch, 102 images 640x480, ~500 segments, single B200).  With N > 1
+(launched by torch.distributed.run, one rank per GPU) every rank runs its own
+batch of the same shape: images are independent, so there is no data-path
+collective (weak scaling); the only exchange is the timing reduction.
+
+value    : whole-job images/s with the batch already resident in HBM (device
+           time from CUDA events on the launching stream, max over ranks).
+e2e      : same metric through the public API from pinned HOST buffers, H2D and
+           D2H inside the timed region.
+roofline : dominant kernel of the step vs the measured peak in MEASURED_PEAKS.json.
+cpu_baseline / --impl reference : the CPU oracle (numpy/torch restatement of the
+           reference path, oracle/) on a bounded sample of the same batch.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from vanishing_points_2017_b200 import synth  # noqa: E402
+
+METRIC = "images/sec end-to-end (lines->VPs)"
+UNIT = "images/s"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+# algorithmic MACs per image of cnn/deploy.prototxt
+CNN_MACS = {"gemm_conv1": 175_738_464, "gemm_conv2": 1_143_091_200, "gemm_conv3": 796_262_400,
+            "gemm_conv4": 597_196_800, "gemm_conv5": 398_131_200, "gemm_fc6": 235_929_600,
+            "gemm_fc7": 16_777_216, "gemm_fc8": 1_638_400}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            d["_source"] = "measured"
+            return d
+        except Exception:
+            pass
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback"
+    return d
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=3)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def make_workload(cfg, rank, n_images=None):
+    """The batch of config `cfg` for this rank (rank r draws seeds disjoint from rank 0's)."""
+    name, B = synth.CONFIGS[cfg][0], synth.CONFIGS[cfg][1]
+    if n_images is not None:
+        B = n_images
+    n, asp = synth.config_sizes(cfg, B)
+    segs = []
+    for idx in range(B):
+        sc = synth.make_scene(1_000_003 * cfg + 100_000 * rank + idx, int(n[idx]), asp[idx][0], asp[idx][1])
+        segs.append(sc["segments"])
+    off = np.zeros(B + 1, dtype=np.int32)
+    off[1:] = np.cumsum(n)
+    return name, np.concatenate(segs, axis=0), off
+
+
+# ------------------------------------------------------------------ CPU oracle arm
+def oracle_pipeline(seg, off, idx, weights, biases):
+    """The CPU restatement of the reference path on images `idx`: numpy sphere votes,
+    torch-CPU fp32 CNN, numpy EM (oracle/)."""
+    from oracle import cnn_oracle, sphere_oracle, vp_oracle
+    n_ok = 0
+    for i in idx:
+        s = seg[off[i]:off[i + 1]]
+        lines = synth.lines_from_segments(s)
+        img = sphere_oracle.votes_to_image(sphere_oracle.sphere_votes(lines, 500))
+        sig, _ = cnn_oracle.forward(img[None], weights, biases)
+        try:
+            res = vp_oracle.expectation_maximisation(lines, s.copy(), sig[0], sphere_image=img)
+            n_ok += res["vp"] is not None
+        except ValueError:
+            pass
+    return n_ok
+
+
+def time_oracle(seg, off, weights, biases, sample, repeats=1):
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    idx = np.linspace(0, len(off) - 2, sample).astype(int)
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        oracle_pipeline(seg, off, idx, weights, biases)
+    dt = (time.perf_counter() - t0) / repeats
+    return sample / dt, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU path on the box's host cores, rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import cnn_oracle
+    name, seg, off = make_workload(args.config, 0)
+    ws, bs = cnn_oracle.random_weights(0, scale=args.weight_scale)
+    sample = 2
+    for _ in range(args.warmup):
+        time_oracle(seg, off, ws, bs, sample)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        time_oracle(seg, off, ws, bs, sample)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = sample / dt
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s-shaped synthetic batch (BASELINE.json configs[%d])" % (name, args.config - 1),
+                       "sample": "%d images per step, evenly spaced over the %d-image batch" % (sample, len(off) - 1)},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d images/step of the same batch; numpy+torch CPU oracle (oracle/), "
+                                       "BLAS/torch threads = %d" % (sample, cores)},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from vanishing_points_2017_b200 import cnn as vcnn, pipeline
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    peaks = load_peaks()
+    name, seg, off = make_workload(args.config, rank, args.images)
+    B = len(off) - 1
+    ws, bs = vcnn.random_weights(0, scale=args.weight_scale)
+    pipe = pipeline.Pipeline(local_rank, ws, bs, sphere_mode=args.sphere_mode)
+    ctx = pipe.ctx
+
+    # pinned host inputs for the end-to-end leg
+    seg_pin = torch.from_numpy(seg).pin_memory()
+    off_pin = torch.from_numpy(off).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        ctx.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def flush_l2():
+        flush.zero_()
+        torch.cuda.synchronize()
+
+    # ---- resident leg: `value`
+    pipe.upload(seg_pin.numpy(), off_pin.numpy())
+    for _ in range(args.warmup):
+        pipe.run()
+    ctx.profile_reset()
+    ctx.profile_enable(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    launches0 = ctx.launch_count()
+    dev_ms, stage = 0.0, {"sphere": 0.0, "cnn": 0.0, "em": 0.0}
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush_l2()
+        pipe.run()
+        ms = pipe.stage_ms()
+        dev_ms += ms["total"]
+        for k in stage:
+            stage[k] += ms[k]
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.summary()
+    ctx.profile_enable(False)
+    prof = ctx.profile_read()
+    results = pipe.fetch(raw=True)
+    n_ok = int(np.sum(results["status"] == 0))
+
+    # ---- end-to-end leg from pinned host buffers: `e2e`
+    for _ in range(max(1, args.warmup // 2)):
+        pipe(seg_pin.numpy(), off_pin.numpy(), raw=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush_l2()
+        out = pipe(seg_pin.numpy(), off_pin.numpy(), raw=True)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    h2d = seg.nbytes + off.nbytes
+    d2h = sum(a.nbytes for a in out.values() if a is not None)
+
+    # ---- reduce over ranks: max time, total images
+    t = torch.tensor([dev_ms / args.steps, e2e_ms, wall_ms / args.steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, e2e_step, wall_step = [float(x) for x in t.tolist()]
+    total_images = B * world
+
+    if rank == 0:
+        # dominant kernel and its roofline
+        top = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else (None, None)
+        roof = None
+        if top[0] is not None:
+            kname, k = top
+            avg_ms = k["ms"] / max(k["launches"], 1)
+            per_step_launches = k["launches"] / args.steps
+            if kname.startswith("gemm_"):
+                flops = 2.0 * CNN_MACS.get(kname, 0) * B / per_step_launches
+                ach = flops / (avg_ms * 1e-3) / 1e12
+                peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+                roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                        "traffic": None}
+            else:
+                # HBM-bound kernels: algorithmic bytes per launch
+                n = np.diff(off).astype(np.float64)
+                if kname == "em_persistent":
+                    it = results["iterations"].astype(np.float64)
+                    # per image: write N^2 similarities once, stream them once per weight-matrix
+                    # product; products per image = initial + 2 per iteration incl. the E-step-only pass
+                    # is not counted + 4 in the final stage (DESIGN.md section "EM roofline")
+                    prods = 1.0 + (it + 1.0) + 4.0
+                    byt = float(np.sum(8.0 * n * n * (1.0 + prods)))
+                elif kname == "sphere_votes":
+                    byt = float(np.sum(24.0 * n) + 4.0 * 500 * 500 * B)
+                else:
+                    byt = 0.0
+                ach = byt / (avg_ms * 1e-3) / 1e9
+                roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": ach / peaks["hbm_gbs"], "traffic": None}
+            roof["kernel"] = kname
+            roof["avg_launch_ms"] = avg_ms
+            roof["peak_source"] = peaks["_source"]
+        kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps}
+                   for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+        # CNN aggregate tensor-pipe fraction
+        gemm_ms = sum(v["ms"] for k, v in prof.items() if k.startswith("gemm_")) / args.steps
+        cnn_tflops = (2.0 * sum(CNN_MACS.values()) * B / (gemm_ms * 1e-3) / 1e12) if gemm_ms > 0 else None
+
+        # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            sample = min(B, args.cpu_sample)
+            v, dt = time_oracle(seg, off, ws, bs, sample)
+            cores = os.cpu_count() or 1
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "%d of the %d images (evenly spaced), %.1f s; numpy+torch CPU oracle (oracle/), "
+                             "BLAS/torch threads = %d" % (sample, B, dt, cores)}
+
+        line = {
+            "metric": METRIC, "value": total_images / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (sphere, EM) + bf16/f32-accumulate (CNN)",
+            "data": "synthetic",
+            "config": {"workload": "%s-shaped synthetic batch (BASELINE.json configs[%d])" % (name, args.config - 1),
+                       "images_per_gpu": B, "segments_per_image_mean": float(np.mean(np.diff(off))),
+                       "sphere_size": 500, "sphere_mode": args.sphere_mode, "cnn_weights": "random-init "
+                       "(train_val.prototxt fillers x%g, seed 0)" % args.weight_scale,
+                       "l2": "flushed between steps (256 MiB memset)", "parallelism": "images sharded, no collective"},
+            "e2e": {"value": total_images / (e2e_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_step},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "stages_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+            "kernels": kernels,
+            "cnn_tflops": cnn_tflops,
+            "wall_ms_per_step": wall_step,
+            "images_with_vps": n_ok,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
+    ap.add_argument("--images", type=int, default=None, help="override the number of images per GPU")
+    ap.add_argument("--sphere-mode", default="votes", choices=["votes", "curves"])
+    ap.add_argument("--weight-scale", type=float, default=1.0,
+                    help="multiplier on the train_val.prototxt filler std (1.0 = the prototxt's own)")
+    ap.add_argument("--cpu-sample", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3          # timing rule: at least 3 warm-up steps
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,71 @@
+"""The resident pipeline equals the three stages called one by one, and the
+stages equal their oracles on the pipeline's own intermediates."""
+import numpy as np
+import pytest
+
+from oracle import cnn_oracle, sphere_oracle as so, vp_oracle as vo
+from vanishing_points_2017_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pipe():
+    from vanishing_points_2017_b200 import pipeline
+    ws, bs = cnn_oracle.random_weights(0, scale=3.0)
+    return pipeline.Pipeline(0, ws, bs), ws, bs
+
+
+def test_pipeline_matches_stagewise_oracles(pipe):
+    p, ws, bs = pipe
+    batch = synth.make_batch(2, n_images=5)
+    res, sig, sph = p(batch["segments"], batch["offsets"], want_response=True, want_sphere=True)
+    off = batch["offsets"]
+    for b in range(5):
+        lines = batch["lines"][off[b]:off[b + 1]]
+        segs = batch["segments"][off[b]:off[b + 1]]
+        # stage 1: bit-exact image
+        np.testing.assert_array_equal(sph[b], so.votes_to_image(so.sphere_votes(lines, 500)))
+    # stage 2: same weights, fp32 oracle
+    rsig, rlog = cnn_oracle.forward(sph, ws, bs)
+    np.testing.assert_allclose(sig, rsig, atol=0.25 * 1e-2 * float(np.max(np.abs(rlog))) + 1e-6)
+    # stage 3: oracle EM on the pipeline's own sphere image and response
+    for b in range(5):
+        lines = batch["lines"][off[b]:off[b + 1]].copy()
+        segs = batch["segments"][off[b]:off[b + 1]].copy()
+        try:
+            ref = vo.expectation_maximisation(lines, segs, sig[b].copy(), sphere_image=sph[b])
+        except ValueError:
+            ref = {"vp": None}
+        if ref["vp"] is None:
+            assert res[b]["vp"] is None
+            continue
+        assert res[b]["vp"].shape == ref["vp"].shape
+        ang = np.arccos(np.minimum(np.abs(np.sum(res[b]["vp"] * ref["vp"], axis=1)), 1.0))
+        assert ang.max() < 1e-4
+        np.testing.assert_array_equal(res[b]["counts"], ref["counts"])
+    ms = p.stage_ms()
+    assert ms["total"] > 0 and abs(ms["sphere"] + ms["cnn"] + ms["em"] - ms["total"]) < 0.05 * ms["total"] + 0.1
+
+
+def test_pipeline_is_deterministic_and_shard_invariant(pipe):
+    from vanishing_points_2017_b200 import pipeline
+    p, _, _ = pipe
+    batch = synth.make_batch(4, n_images=12)
+    full = p(batch["segments"], batch["offsets"])
+    again = p(batch["segments"], batch["offsets"])
+    for a, b in zip(full, again):
+        assert (a["vp"] is None) == (b["vp"] is None)
+        if a["vp"] is not None:
+            np.testing.assert_array_equal(a["vp"], b["vp"])
+    # sharded over 3 "ranks" (same GPU here) and gathered: identical per-image results
+    got = [None] * 12
+    for r in range(3):
+        idx = pipeline.shard_batch(batch["offsets"], 3, r)
+        seg, off = pipeline.take_images(batch["segments"], batch["offsets"], idx)
+        part = pipeline.gather_results(p(seg, off), idx, 12, 1)
+        for i in idx:
+            got[i] = part[i]
+    for a, b in zip(full, got):
+        if a["vp"] is not None:
+            np.testing.assert_array_equal(a["vp"], b["vp"])

@@ -1,0 +1,64 @@
+"""Host-side logic of the multi-GPU path on CPU: partitioning, sub-batching and
+the final result gather with torch.distributed (gloo, world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import torch.multiprocessing as mp
+
+from vanishing_points_2017_b200 import pipeline, synth
+
+
+def test_shards_partition_the_batch_and_balance_cost():
+    n, _ = synth.config_sizes(4, 400)
+    off = np.concatenate([[0], np.cumsum(n)])
+    for ws in (1, 2, 4, 8):
+        parts = [pipeline.shard_batch(off, ws, r) for r in range(ws)]
+        allidx = np.sort(np.concatenate(parts))
+        np.testing.assert_array_equal(allidx, np.arange(400))
+        loads = np.array([pipeline.image_cost(n[p]).sum() for p in parts])
+        assert loads.max() / loads.mean() < 1.02
+
+
+def test_take_images_roundtrip():
+    b = synth.make_batch(2, n_images=6)
+    idx = np.array([4, 1, 5])
+    seg, off = pipeline.take_images(b["segments"], b["offsets"], idx)
+    for k, i in enumerate(idx):
+        np.testing.assert_array_equal(seg[off[k]:off[k + 1]], b["segments"][b["offsets"][i]:b["offsets"][i + 1]])
+    seg0, off0 = pipeline.take_images(b["segments"], b["offsets"], np.array([], dtype=int))
+    assert seg0.shape == (0, 4) and off0.tolist() == [0]
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_images = 11
+    off = np.concatenate([[0], np.cumsum(np.arange(100, 100 + n_images))])
+    idx = pipeline.shard_batch(off, world, rank)
+    local = [{"vp": np.full((1, 3), float(i)), "rank": rank} for i in idx]
+    out = pipeline.gather_results(local, idx, n_images, world, dist)
+    if rank == 0:
+        q.put([(int(r["vp"][0, 0]), r["rank"]) for r in out])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_results_gloo_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [g[0] for g in got] == list(range(11))
+    assert {g[1] for g in got} == {0, 1}

@@ -182,8 +182,8 @@ __device__ __forceinline__ int sample_row(int k, double step, double l0, double 
 // samples and the samples bracketing alpha* need evaluating.  The interval is
 // recorded in a per-image difference array (+1 at rmin, -1 at rmax+1).
 __global__ void sphere_curves_kernel(const double* __restrict__ lines, const int32_t* __restrict__ offsets, int B, int S,
-                                     const int32_t* __restrict__ first, double f, int32_t* __restrict__ diff) {
-    const int64_t line = blockIdx.x;
+                                     const int32_t* __restrict__ first, double f, int32_t* __restrict__ diff, int64_t line0) {
+    const int64_t line = line0 + blockIdx.x;
     __shared__ int s_img;
     if (threadIdx.x == 0) {
         int lo = 0, hi = B;           // largest b with offsets[b] <= line
@@ -261,7 +261,7 @@ int sphere_map_dev(vpk_ctx* ctx, const double* d_lines, const int32_t* d_offsets
                    int32_t B, int32_t S, int32_t mode, double alpha, const double* d_weights,
                    uint32_t* d_hist, unsigned long long* d_whist, uint8_t* d_img) {
     const int64_t plane = (int64_t)S * S;
-    const int64_t sumN = h_offsets[B];
+    const int64_t sumN = h_offsets[B] - h_offsets[0];      // offsets may be a window of a larger batch
     if (mode == VPK_SPHERE_VOTES) {
         // work list of upper-triangular tile pairs
         int64_t items = 0;
@@ -327,7 +327,7 @@ int sphere_map_dev(vpk_ctx* ctx, const double* d_lines, const int32_t* d_offsets
             KernelScope ks(ctx, "sphere_curves");
             int threads = S >= 512 ? 512 : ((S + 31) / 32) * 32;
             sphere_curves_kernel<<<(unsigned)sumN, threads, 0, ctx->stream>>>(d_lines, d_offsets, B, S, d_first, 1.0,
-                                                                               ctx->d_misc.as<int32_t>());
+                                                                               ctx->d_misc.as<int32_t>(), (int64_t)h_offsets[0]);
             VPK_TRY(check_launch("sphere_curves"));
         }
         {

@@ -1,0 +1,122 @@
+"""The whole hot path for a ragged batch, and its sharding over the GPUs of one box.
+
+segments -> lines -> sphere image -> CNN -> EM -> VPs with every intermediate
+resident in HBM (reference example.py:37-39 / benchmark.py:59-66, which
+round-trip through per-image pickles instead).  Images are independent
+(reference loops per file: evaluation.py:126, 271, 309), so multi-GPU is a
+cost-balanced partition of the batch with no collective on the data path; the
+only exchange is the final gather of the small per-image results.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from . import cnn as _cnn
+from .vp_localisation import _alloc_result, unpack_results
+
+
+class Pipeline:
+    """One context (GPU) running the path; CNN weights loaded once."""
+
+    def __init__(self, device=0, weights=None, biases=None, mean=None, sphere_mode="votes", alpha=0.1, size=500,
+                 **em_kwargs):
+        self.ctx = _lib.default_context(device)
+        if weights is None:
+            weights, biases = _cnn.random_weights(0)
+        self.net = _cnn.Net(self.ctx, weights, biases)
+        if mean is not None:
+            self.net.set_mean(mean)
+        self.mode = {"votes": _lib.SPHERE_VOTES, "curves": _lib.SPHERE_CURVES}[sphere_mode]
+        self.alpha = float(alpha)
+        self.size = int(size)
+        self.cfg = _lib.em_config(**em_kwargs)
+        self._B = 0
+        self._off = None
+
+    # -- the three steps of include/vpk.h, so callers can time them separately
+    def upload(self, segments, offsets):
+        seg = _lib.as_f64(segments, 4)
+        off = _lib.as_offsets(offsets)
+        if off[-1] != seg.shape[0]:
+            raise ValueError("offsets[-1] must equal the number of segments")
+        self._B, self._off = off.size - 1, off
+        _lib.check(self.ctx.lib.vpk_pipeline_upload(self.ctx.h, _lib.ptr(seg), _lib.ptr(off), self._B),
+                   "vpk_pipeline_upload")
+
+    def run(self):
+        _lib.check(self.ctx.lib.vpk_pipeline_run(self.ctx.h, self.size, self.mode, self.alpha, C.byref(self.cfg)),
+                   "vpk_pipeline_run")
+
+    def fetch(self, want_response=False, want_sphere=False, raw=False):
+        arrs, res = _alloc_result(self._B, int(self._off[-1]), False)
+        sig = np.empty((self._B, 20, 20), np.float32) if want_response else None
+        sph = np.empty((self._B, self.size, self.size), np.uint8) if want_sphere else None
+        _lib.check(self.ctx.lib.vpk_pipeline_fetch(self.ctx.h, C.byref(res), _lib.ptr(sig), _lib.ptr(sph)),
+                   "vpk_pipeline_fetch")
+        out = arrs if raw else unpack_results(arrs, self._off)
+        return (out, sig, sph) if (want_response or want_sphere) else out
+
+    def stage_ms(self):
+        ms = (C.c_float * 4)()
+        _lib.check(self.ctx.lib.vpk_pipeline_stage_ms(self.ctx.h, ms), "vpk_pipeline_stage_ms")
+        return {"sphere": ms[0], "cnn": ms[1], "em": ms[2], "total": ms[3]}
+
+    def __call__(self, segments, offsets, **fetch_kw):
+        """End to end from host buffers (H2D, path, D2H)."""
+        self.upload(segments, offsets)
+        self.run()
+        return self.fetch(**fetch_kw)
+
+
+def image_cost(n):
+    """Relative cost model of one image: the O(N^2) pair/weight-matrix work
+    dominates, plus the constant CNN cost expressed in the same unit."""
+    n = np.asarray(n, dtype=np.float64)
+    return n * n + 250_000.0
+
+
+def shard_batch(offsets, world_size, rank):
+    """Cost-balanced partition: images sorted by descending cost are dealt to
+    the currently lightest rank (LPT).  Returns the sorted image indices of `rank`."""
+    n = np.diff(np.asarray(offsets, dtype=np.int64))
+    cost = image_cost(n)
+    order = np.argsort(-cost, kind="stable")
+    load = np.zeros(world_size)
+    owner = np.empty(len(n), dtype=np.int64)
+    for i in order:
+        r = int(np.argmin(load))
+        owner[i] = r
+        load[r] += cost[i]
+    return np.sort(np.where(owner == rank)[0])
+
+
+def take_images(segments, offsets, idx):
+    """Sub-batch (segments, offsets) of the images `idx`."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    segs = [segments[offsets[i]:offsets[i + 1]] for i in idx]
+    n = np.array([s.shape[0] for s in segs], dtype=np.int64)
+    off = np.zeros(len(idx) + 1, dtype=np.int32)
+    off[1:] = np.cumsum(n)
+    seg = np.concatenate(segs, axis=0) if segs else np.zeros((0, 4))
+    return np.ascontiguousarray(seg), off
+
+
+def gather_results(local_results, idx, n_images, world_size, dist=None):
+    """Final result gather (rank 0 gets the full list): the only inter-rank
+    exchange of the path.  `dist` is torch.distributed or None (single rank)."""
+    if dist is None or world_size == 1:
+        out = [None] * n_images
+        for i, r in zip(idx, local_results):
+            out[int(i)] = r
+        return out
+    payload = [(int(i), r) for i, r in zip(idx, local_results)]
+    gathered = [None] * world_size if dist.get_rank() == 0 else None
+    dist.gather_object(payload, gathered, dst=0)
+    if dist.get_rank() != 0:
+        return None
+    out = [None] * n_images
+    for part in gathered:
+        for i, r in part:
+            out[i] = r
+    return out
