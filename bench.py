@@ -245,6 +245,8 @@ def run_ours(args, rank, world, local_rank):
 
     if rank == 0:
         # dominant kernel and its roofline
+        em_phases = {k[3:]: v["ms"] for k, v in prof.items() if k.startswith("em:")}
+        prof = {k: v for k, v in prof.items() if not k.startswith("em:")}
         top = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else (None, None)
         roof = None
         if top[0] is not None:
@@ -312,6 +314,8 @@ def run_ours(args, rank, world, local_rank):
             "stages_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "kernels": kernels,
             "cnn_tflops": cnn_tflops,
+            "em_phase_share": ({k: v / max(sum(em_phases.values()), 1e-9) for k, v in em_phases.items()}
+                               if em_phases else None),
             "wall_ms_per_step": wall_step,
             "images_with_vps": n_ok,
         }

@@ -510,10 +510,14 @@ def expectation_maximisation(l, lp, cnn_response, num_iter=100, sphere_image=Non
             if do_merge:
                 cur, nxt, s = merge_vps(cur, nxt, s, l, merge_thresh * 10, lweight, lsim, colsum,
                                         wbias, pdfpar, lp)                       # :339
+            if trace is not None:
+                trace.append(("final_merged", cur.copy(), nxt.copy(), s.copy()))
             p = estep(cur)                                                       # :344 (index i, sic)
             w = wmat(p)
             rem = []
             assoc = np.argmax(w, axis=0)
+            if trace is not None:
+                trace.append(("final_assoc", np.bincount(assoc, minlength=cur.shape[0])))
             for m in range(cur.shape[0]):
                 sel = assoc == m
                 if not np.any(sel):
@@ -532,12 +536,16 @@ def expectation_maximisation(l, lp, cnn_response, num_iter=100, sphere_image=Non
                     if err > 1.5:
                         rem.append(m)
             rem = np.array(rem, dtype=int)
+            if trace is not None:
+                trace.append(("final_refit_removed", rem.copy(), nxt.copy(), s.copy()))
             cur, nxt, s = np.delete(cur, rem, 0), np.delete(nxt, rem, 0), np.delete(s, rem, 0)
             p = estep(cur)                                                       # :398
             dm = wmat(p)
             if dm.size <= 0:
                 return result
             good = np.unique(np.argmax(dm, axis=0))                              # :406-408
+            if trace is not None:
+                trace.append(("final_good", good.copy(), np.bincount(np.argmax(dm, axis=0), minlength=cur.shape[0])))
             cur, nxt, s = cur[good], nxt[good], s[good]
             p = estep(nxt)                                                       # :415 (index i+1)
             dm = wmat(p)

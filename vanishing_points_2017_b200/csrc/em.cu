@@ -53,8 +53,13 @@ struct EmParams {
     double* overflow;      // shared clustering scratch for very large splits
     size_t overflow_cap;   // doubles
     int* overflow_lock;
+    unsigned long long* phase_cycles;   // nullable: per-phase SM cycles summed over CTAs (profiling)
     EmDeviceOut out;
 };
+
+enum { PH_SETUP = 0, PH_PAIR, PH_RATING, PH_INIT, PH_ESTEP, PH_WMAT, PH_MSTEP, PH_MERGE, PH_SPLIT, PH_COUNTS, PH_OTHER, PH_N };
+static const char* const kPhaseNames[PH_N] = {"em:setup", "em:pair_pass", "em:line_rating", "em:init", "em:estep", "em:wmat",
+                                             "em:mstep", "em:merge", "em:split", "em:counts", "em:other"};
 
 // per-image view of the slot workspace
 struct Img {
@@ -86,7 +91,19 @@ struct EmShared {
     double sigma_prior;
     int M, npdf, img, flag, ia, ib;
     double da;
+    unsigned long long phase[PH_N];   // profiling: SM cycles per phase of this CTA
+    long long t_last;
+    int timing;
 };
+
+// attribute the cycles since the previous lap to phase `ph` (thread 0 only, profiling runs only)
+__device__ __forceinline__ void phase_lap(EmShared& sh, int ph) {
+    if (sh.timing && threadIdx.x == 0) {
+        long long t = clock64();
+        sh.phase[ph] += (unsigned long long)(t - sh.t_last);
+        sh.t_last = t;
+    }
+}
 
 // ---------------------------------------------------------------------------
 // small device helpers
@@ -200,7 +217,8 @@ __device__ __forceinline__ double proximity(const Seg& a, const Seg& b, double d
 // ---------------------------------------------------------------------------
 // E3: lsim = cos9 * prox, symmetric, zero diagonal; column sums
 // ---------------------------------------------------------------------------
-__device__ void pair_pass(const Img& im) {
+__device__ void pair_pass(const Img& im, EmShared& sh) {
+    phase_lap(sh, PH_OTHER);
     const int N = im.N;
     const int T = (N + 31) / 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -232,12 +250,15 @@ __device__ void pair_pass(const Img& im) {
         for (int j = 0; j < N; ++j) acc += im.lsim[(size_t)j * N + k];
         im.colsum[k] = acc;
     }
+    __syncthreads();
+    phase_lap(sh, PH_PAIR);
 }
 
 // ---------------------------------------------------------------------------
 // E4: kNN line rating (vp_localisation.py:34-84), one warp per line
 // ---------------------------------------------------------------------------
 __device__ void line_rating(const Img& im, EmShared& sh, bool use_weights) {
+    phase_lap(sh, PH_OTHER);
     const int N = im.N;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k1 = min(10, N), k2 = min(4, N);
@@ -305,6 +326,7 @@ __device__ void line_rating(const Img& im, EmShared& sh, bool use_weights) {
         __syncwarp();
     }
     __syncthreads();
+    phase_lap(sh, PH_RATING);
 }
 
 // ---------------------------------------------------------------------------
@@ -434,6 +456,7 @@ __device__ void init_prior_and_vps(const EmParams& P, int b, EmShared& sh, bool 
 // E5: E-step (probability_functions.py:99-147).  v = sh.cur or sh.nxt.
 // ---------------------------------------------------------------------------
 __device__ void estep(const Img& im, EmShared& sh, const double (*v)[3]) {
+    phase_lap(sh, PH_OTHER);
     const int M = sh.M, N = im.N, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // prior at the VP angles: calc_angles (:252-259) + calc_pdf (:8-40)
     for (int m = warp; m < M; m += kEmWarps) {
@@ -487,12 +510,14 @@ __device__ void estep(const Img& im, EmShared& sh, const double (*v)[3]) {
             im.pvl[(size_t)m * N + n] = im.pvl[(size_t)m * N + n] * sh.pv[m] / pl;   // calc_pvl (:128)
     }
     __syncthreads();
+    phase_lap(sh, PH_ESTEP);
 }
 
 // ---------------------------------------------------------------------------
 // E6: weight matrix (vp_localisation.py:515-524) as an (M x N)(N x N) product
 // ---------------------------------------------------------------------------
 __device__ void wmat(const Img& im, EmShared& sh, double bias, bool use_weights) {
+    phase_lap(sh, PH_OTHER);
     const int M = sh.M, N = im.N, tid = threadIdx.x;
     for (int m0 = 0; m0 < M; m0 += kMCH) {
         const int mc = min(kMCH, M - m0);
@@ -542,6 +567,7 @@ __device__ void wmat(const Img& im, EmShared& sh, double bias, bool use_weights)
         }
     }
     __syncthreads();
+    phase_lap(sh, PH_WMAT);
 }
 
 // assoc[n] = argmax_m w[m,n] (first maximum, numpy.argmax; NaN counts as max)
@@ -563,6 +589,7 @@ __device__ void argmax_assoc(const Img& im, EmShared& sh) {
 // E9: calc_vp_line_counts (vp_localisation.py:482-512).  lvsq must have been
 // computed (estep) for the same VP set that is being counted.
 __device__ void line_counts(const Img& im, EmShared& sh, double thresh) {
+    phase_lap(sh, PH_OTHER);
     const int M = sh.M, N = im.N, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     argmax_assoc(im, sh);
     for (int n = tid; n < N; n += kEmThreads) {
@@ -581,6 +608,7 @@ __device__ void line_counts(const Img& im, EmShared& sh, double thresh) {
         if (lane == 0) { sh.cnt[m] = c; sh.cw[m] = cw; }
     }
     __syncthreads();
+    phase_lap(sh, PH_COUNTS);
 }
 
 // E7 + E8 for VP m by one warp: smallest eigenvector of sum (w/max w)^2 l l^T
@@ -601,16 +629,39 @@ __device__ bool refit_vp(const Img& im, const double* wrow, const double* wrow2,
     any = __any_sync(0xffffffffu, any);
     if (!any || mx == 0.0 || isnan(mx) || isinf(mx)) return false;      // :456-460 / LinAlgError
     double g[6] = {0, 0, 0, 0, 0, 0};
+    int rows = 0, only = -1;
     for (int n = lane; n < N; n += 32) {
         if (sel >= 0 && im.assoc[n] != sel) continue;
         double x = (wrow[n] + (wrow2 ? wrow2[n] : 0.0)) / mx;
         double a = x * im.ln[3 * (size_t)n], b = x * im.ln[3 * (size_t)n + 1], c = x * im.ln[3 * (size_t)n + 2];
         g[0] += a * a; g[1] += a * b; g[2] += a * c; g[3] += b * b; g[4] += b * c; g[5] += c * c;
+        ++rows; only = n;
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) g[k] = warp_sum(g[k]);
+    for (int o = 16; o > 0; o >>= 1) {
+        rows += __shfl_xor_sync(0xffffffffu, rows, o);
+        only = max(only, __shfl_xor_sync(0xffffffffu, only, o));
+    }
     double e[3];
-    bool okv = smallest_eigvec3(g, e);
+    bool okv;
+    if (rows == 1) {
+        // A single 1x3 row has a 2-D null space; LAPACK's full SVD (what numpy.linalg.svd runs,
+        // vp_localisation.py:466) completes V with the Householder reflector of dgelqf/dlarfg:
+        // V[:,2] = row 3 of H = I - tau v v^T, v = (1, a2/(a1-beta), a3/(a1-beta)).
+        double x = (wrow[only] + (wrow2 ? wrow2[only] : 0.0)) / mx;
+        double a1 = x * im.ln[3 * (size_t)only], a2 = x * im.ln[3 * (size_t)only + 1], a3 = x * im.ln[3 * (size_t)only + 2];
+        double nrm = sqrt(a1 * a1 + a2 * a2 + a3 * a3);
+        double beta = -copysign(nrm, a1);
+        double tau = (beta - a1) / beta;
+        double v2 = a2 / (a1 - beta), v3 = a3 / (a1 - beta);
+        e[0] = -tau * v3; e[1] = -tau * v3 * v2; e[2] = 1.0 - tau * v3 * v3;
+        double n2 = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+        okv = n2 > 0.0 && !isnan(n2);
+        if (okv) { e[0] /= n2; e[1] /= n2; e[2] /= n2; }
+    } else {
+        okv = smallest_eigvec3(g, e);
+    }
     if (!okv) return false;
     double sg = sign_np(e[2]);                                           // :474
     out[0] = e[0] * sg; out[1] = e[1] * sg; out[2] = e[2] * sg;
@@ -654,6 +705,7 @@ __device__ void compact_vps(EmShared& sh) {
 // E10: merge_vps (vp_localisation.py:633-684) on the sh.nxt row set
 // ---------------------------------------------------------------------------
 __device__ void merge_vps(const Img& im, EmShared& sh, const EmParams& P, double thresh) {
+    phase_lap(sh, PH_OTHER);
     const int tid = threadIdx.x, warp = tid >> 5;
     while (true) {
         __syncthreads();
@@ -701,6 +753,7 @@ __device__ void merge_vps(const Img& im, EmShared& sh, const EmParams& P, double
         compact_vps(sh);
     }
     __syncthreads();
+    phase_lap(sh, PH_MERGE);
 }
 
 // ---------------------------------------------------------------------------
@@ -947,6 +1000,11 @@ __global__ void __launch_bounds__(kEmThreads, 2) em_kernel(EmParams P) {
     const vpk_em_config& cfg = P.cfg;
     const double max_stdd = 1e-6;            // angle mode (:197)
     double* slot = P.ws + (size_t)blockIdx.x * P.ws_stride;
+    if (tid == 0) {
+        sh.timing = P.phase_cycles != nullptr;
+        for (int k = 0; k < PH_N; ++k) sh.phase[k] = 0;
+        sh.t_last = clock64();
+    }
 
     while (true) {
         __syncthreads();
@@ -992,7 +1050,8 @@ __global__ void __launch_bounds__(kEmThreads, 2) em_kernel(EmParams P) {
             im.langle[n] = phi > 0.5 * kPi ? kPi - phi : phi;
         }
         __syncthreads();
-        if (cfg.use_weights) pair_pass(im);
+        phase_lap(sh, PH_SETUP);
+        if (cfg.use_weights) pair_pass(im, sh);
         else {
             for (int n = tid; n < N; n += kEmThreads) im.colsum[n] = 0.0;
         }
@@ -1001,7 +1060,9 @@ __global__ void __launch_bounds__(kEmThreads, 2) em_kernel(EmParams P) {
 
         // ---- initial hypotheses and prior
         const bool have_init = P.init_vp != nullptr;
+        phase_lap(sh, PH_OTHER);
         init_prior_and_vps(P, b, sh, have_init);
+        phase_lap(sh, PH_INIT);
         if (have_init) {
             if (tid == 0) {
                 int i0 = P.init_off[b], i1 = P.init_off[b + 1];
@@ -1037,12 +1098,15 @@ __global__ void __launch_bounds__(kEmThreads, 2) em_kernel(EmParams P) {
             if (i % cfg.split_merge_freq == 0 && i > 0 && i < 100 && cfg.do_split) {     // :262
                 estep(im, sh, sh.cur);
                 wmat(im, sh, cfg.wbias, cfg.use_weights != 0);
+                phase_lap(sh, PH_OTHER);
                 split_best_vp(im, sh, P, cfg.merge_thresh);
+                phase_lap(sh, PH_SPLIT);
             }
             estep(im, sh, sh.cur);                             // :273
             wmat(im, sh, cfg.wbias, cfg.use_weights != 0);     // :282
             // ---- M-step (:284-322), one warp per VP
             const int M = sh.M;
+            phase_lap(sh, PH_OTHER);
             for (int m = warp; m < M; m += kEmWarps) {
                 if (!cfg.do_iterations) {
                     if (lane == 0) { sh.rem[m] = 0; sh.err[m] = 0.0; for (int c = 0; c < 3; ++c) sh.nxt[m][c] = sh.cur[m][c]; }
@@ -1084,6 +1148,7 @@ __global__ void __launch_bounds__(kEmThreads, 2) em_kernel(EmParams P) {
             }
             __syncthreads();
             const double max_err = sh.da;
+            phase_lap(sh, PH_MSTEP);
             compact_vps(sh);
             estep(im, sh, sh.cur);                             // :332 (index i, with the new variances)
 
@@ -1166,13 +1231,17 @@ __global__ void __launch_bounds__(kEmThreads, 2) em_kernel(EmParams P) {
         }
         write_result(P, b, base, im, sh, status, iters, done && status == VPK_EM_OK);
     }
+    if (tid == 0 && sh.timing) {
+        phase_lap(sh, PH_OTHER);
+        for (int k = 0; k < PH_N; ++k) atomicAdd(P.phase_cycles + k, sh.phase[k]);
+    }
 }
 
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 struct EmState {
-    DBuf ws, order, queue, overflow, resp, out_small, out_assoc, out_dm, init_vp, init_off, sphere;
+    DBuf ws, order, queue, overflow, resp, out_small, out_assoc, out_dm, init_vp, init_off, sphere, phase;
 };
 
 void em_free(vpk_ctx* ctx) {
@@ -1180,7 +1249,7 @@ void em_free(vpk_ctx* ctx) {
     EmState* e = ctx->em;
     e->ws.release(); e->order.release(); e->queue.release(); e->overflow.release(); e->resp.release();
     e->out_small.release(); e->out_assoc.release(); e->out_dm.release(); e->init_vp.release(); e->init_off.release();
-    e->sphere.release();
+    e->sphere.release(); e->phase.release();
     delete e;
     ctx->em = nullptr;
 }
@@ -1225,12 +1294,31 @@ int em_dev(vpk_ctx* ctx, const double* d_lines, const double* d_segments, const 
     P.ws = st->ws.as<double>(); P.ws_stride = stride; P.nmax = nmax;
     P.overflow = st->overflow.as<double>(); P.overflow_cap = ov; P.overflow_lock = st->queue.as<int>() + 1;
     P.out = out;
+    P.phase_cycles = nullptr;
+    if (ctx->profiling) {
+        VPK_TRY(st->phase.ensure(PH_N * sizeof(unsigned long long)));
+        VPK_CUDA(cudaMemsetAsync(st->phase.p, 0, PH_N * sizeof(unsigned long long), ctx->stream));
+        P.phase_cycles = st->phase.as<unsigned long long>();
+    }
     {
         KernelScope ks(ctx, "em_persistent");
         em_kernel<<<grid, kEmThreads, 0, ctx->stream>>>(P);
         VPK_TRY(check_launch("em_persistent"));
     }
     VPK_CUDA(cudaStreamSynchronize(ctx->stream));      // h_stage (order) is reused by later calls
+    if (P.phase_cycles) {
+        // per-phase share of the kernel: CTA-cycles summed over CTAs, reported as "em:<phase>"
+        // pseudo-entries in CTA-milliseconds at the SM clock (not additive with kernel times)
+        unsigned long long h[PH_N];
+        VPK_CUDA(cudaMemcpy(h, st->phase.p, sizeof(h), cudaMemcpyDeviceToHost));
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+        for (int k = 0; k < PH_N; ++k) {
+            auto& e = ctx->prof[kPhaseNames[k]];
+            e.total_ms += (double)h[k] / (khz > 0 ? (double)khz : 1.0e6);
+            e.launches += 1;
+        }
+    }
     return VPK_OK;
 }
 
