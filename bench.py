@@ -195,12 +195,10 @@ def run_ours(args, rank, world, local_rank):
         flush.zero_()
         torch.cuda.synchronize()
 
-    # ---- resident leg: `value`
+    # ---- resident leg: `value` (no per-kernel events inside the timed region)
     pipe.upload(seg_pin.numpy(), off_pin.numpy())
     for _ in range(args.warmup):
         pipe.run()
-    ctx.profile_reset()
-    ctx.profile_enable(True)
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -218,10 +216,22 @@ def run_ours(args, rank, world, local_rank):
     wall_ms = (time.perf_counter() - t0) * 1e3
     launches = ctx.launch_count() - launches0
     clocks = sampler.summary()
-    ctx.profile_enable(False)
-    prof = ctx.profile_read()
     results = pipe.fetch(raw=True)
     n_ok = int(np.sum(results["status"] == 0))
+
+    # ---- profiled leg: the same steps again with CUDA events around every kernel launch (on the
+    # library's stream) -> per-kernel times, the dominant kernel and its roofline
+    psteps = max(1, min(args.steps, 5))
+    ctx.profile_reset()
+    ctx.em_stats(reset=True)
+    ctx.profile_enable(True)
+    for _ in range(psteps):
+        flush_l2()
+        pipe.run()
+    barrier()
+    ctx.profile_enable(False)
+    prof = ctx.profile_read()
+    em_stats = ctx.em_stats()
 
     # ---- end-to-end leg from pinned host buffers: `e2e`
     for _ in range(max(1, args.warmup // 2)):
@@ -244,46 +254,53 @@ def run_ours(args, rank, world, local_rank):
     total_images = B * world
 
     if rank == 0:
-        # dominant kernel and its roofline
-        em_phases = {k[3:]: v["ms"] for k, v in prof.items() if k.startswith("em:")}
-        prof = {k: v for k, v in prof.items() if not k.startswith("em:")}
+        # dominant kernel (largest share of the profiled steps) and its roofline
         top = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else (None, None)
         roof = None
-        if top[0] is not None:
-            kname, k = top
+        n = np.diff(off).astype(np.float64)
+
+        def roofline_of(kname, k):
             avg_ms = k["ms"] / max(k["launches"], 1)
-            per_step_launches = k["launches"] / args.steps
             if kname.startswith("gemm_"):
-                flops = 2.0 * CNN_MACS.get(kname, 0) * B / per_step_launches
+                flops = 2.0 * CNN_MACS.get(kname, 0) * B * psteps / k["launches"]
                 ach = flops / (avg_ms * 1e-3) / 1e12
                 peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-                roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                        "traffic": None}
+                r = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak}
             else:
-                # HBM-bound kernels: algorithmic bytes per launch
-                n = np.diff(off).astype(np.float64)
-                if kname == "em_persistent":
-                    it = results["iterations"].astype(np.float64)
-                    # per image: write N^2 similarities once, stream them once per weight-matrix
-                    # product; products per image = initial + 2 per iteration incl. the E-step-only pass
-                    # is not counted + 4 in the final stage (DESIGN.md section "EM roofline")
-                    prods = 1.0 + (it + 1.0) + 4.0
-                    byt = float(np.sum(8.0 * n * n * (1.0 + prods)))
+                # HBM-bound kernels: algorithmic bytes per launch ("Kernels")
+                if kname == "em_wmat":
+                    # 8 N^2 bytes of similarity matrix per per-image product (counted on the device)
+                    byt = em_stats["wmat_bytes"] / max(k["launches"], 1)
+                elif kname == "em_pair":
+                    byt = float(np.sum(8.0 * n * n + 32.0 * n))
                 elif kname == "sphere_votes":
                     byt = float(np.sum(24.0 * n) + 4.0 * 500 * 500 * B)
+                elif kname == "lrn_pool1":
+                    byt = B * (96 * 123 * 123 * 2 + 96 * 61 * 61 * 2.0)
+                elif kname == "lrn_pool2":
+                    byt = B * (256 * 61 * 61 * 2 + 256 * 30 * 30 * 2.0)
                 else:
                     byt = 0.0
                 ach = byt / (avg_ms * 1e-3) / 1e9
-                roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": ach / peaks["hbm_gbs"], "traffic": None}
-            roof["kernel"] = kname
-            roof["avg_launch_ms"] = avg_ms
-            roof["peak_source"] = peaks["_source"]
-        kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps}
+                r = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": ach / peaks["hbm_gbs"]}
+            r.update({"traffic": None, "kernel": kname, "avg_launch_ms": avg_ms, "peak_source": peaks["_source"]})
+            return r
+
+        if top[0] is not None:
+            roof = roofline_of(*top)
+        kernels = {k: {"ms_per_step": v["ms"] / psteps, "launches_per_step": v["launches"] / psteps}
                    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
         # CNN aggregate tensor-pipe fraction
-        gemm_ms = sum(v["ms"] for k, v in prof.items() if k.startswith("gemm_")) / args.steps
+        gemm_ms = sum(v["ms"] for k, v in prof.items() if k.startswith("gemm_")) / psteps
         cnn_tflops = (2.0 * sum(CNN_MACS.values()) * B / (gemm_ms * 1e-3) / 1e12) if gemm_ms > 0 else None
+        em_info = None
+        if "em_wmat" in prof:
+            wm = prof["em_wmat"]
+            em_info = {"supersteps_per_step": em_stats["supersteps"] / psteps,
+                       "wmat_products_per_step": em_stats["wmat_products"] / psteps,
+                       "wmat_algorithmic_GBps": em_stats["wmat_bytes"] / (wm["ms"] * 1e-3) / 1e9,
+                       "wmat_fp64_TFLOPs": em_stats["wmat_flops"] / (wm["ms"] * 1e-3) / 1e12}
 
         # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
         cpu = None
@@ -314,8 +331,7 @@ def run_ours(args, rank, world, local_rank):
             "stages_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "kernels": kernels,
             "cnn_tflops": cnn_tflops,
-            "em_phase_share": ({k: v / max(sum(em_phases.values()), 1e-9) for k, v in em_phases.items()}
-                               if em_phases else None),
+            "em": em_info,
             "wall_ms_per_step": wall_step,
             "images_with_vps": n_ok,
         }

@@ -1,0 +1,1225 @@
+// Stage 3 core: the per-image logic of the EM vanishing-point localisation
+// (reference vp_localisation.py:168-450 and what it calls in
+// probability_functions.py / coordinate_conversion.py), written against a
+// small "team" abstraction so that the very same source is
+//   * the body of the CUDA kernels in em.cu (team = one CTA), and
+//   * a single-threaded host build used ONLY by tests/hostsim (team = 1 thread)
+//     to check the control flow against the golden vectors on a box without a
+//     GPU.  The host build is test infrastructure; libvpk.so never contains it.
+//
+// Execution model (em.cu): every image owns a slot.  The reference's control
+// flow is a sequence of "E-step, weight matrix, then a reduction over the lines
+// and a discrete decision"; it is restated here as a state machine.  One
+// superstep = E kernel (all lines of all active slots) -> W kernel (the
+// (M x N)(N x N) weight-matrix products, tiled over the whole GPU) -> POST
+// kernel (one CTA per slot: reductions, 3x3 eigen-solves, pruning / split /
+// merge decisions, choice of the next superstep).  `phase` says what POST does
+// with the fresh E/W results.
+#pragma once
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+#include "../../include/vpk.h"
+
+#if defined(__CUDACC__)
+#define VPK_DEV __device__ __forceinline__
+#define VPK_DEVFN __device__
+#define VPK_HD __host__ __device__ __forceinline__
+#else
+#include <cmath>
+#define VPK_DEV inline
+#define VPK_DEVFN inline
+#define VPK_HD inline
+#endif
+
+namespace vpk {
+namespace em {
+
+#if !defined(__CUDACC__)
+using std::isinf;
+using std::isnan;
+#endif
+
+constexpr int kMaxM = VPK_MAX_VP;
+constexpr int kMaxComp = 100;              // probability_functions.py:87
+constexpr int kCells = VPK_GRID * VPK_GRID;
+constexpr int kTK = 64;                    // columns per similarity slab (W kernel tile)
+constexpr int kMP = 16;                    // VP rows per weight-matrix pass
+constexpr int kPostThreads = 512;
+constexpr int kK1 = 10;                    // kNN rating: nearest by distance (vp_localisation.py:34)
+constexpr double kPi = 3.141592653589793;
+
+// what POST does with the E/W results of the superstep that just ran
+enum Phase : int32_t {
+    PH_INIT_COUNTS = 0,   // :245-251  counts of the initial hypotheses, drop < 3 lines
+    PH_SPLIT,             // :262-269  split_best_vp
+    PH_MSTEP,             // :284-333  M-step
+    PH_MERGE_EVAL,        // :649-681  one merge trial of merge_vps
+    PH_HARD_REFIT,        // :344-396  hard-assignment refit
+    PH_KEEP_WINNERS,      // :398-413  keep VPs that win a line
+    PH_FINAL_COUNTS,      // :415-437  counts, drop VPs with too few lines
+    PH_DONE,
+    // control states (no E/W needed to enter them)
+    CT_ITER_BEGIN, CT_MERGE_LOOP, CT_ADVANCE, CT_FINAL_A
+};
+
+struct Team { int tid, nthreads, warp, lane, nwarps, lanes; };
+
+#if defined(__CUDACC__)
+VPK_DEV Team make_team() {
+    Team T;
+    T.tid = threadIdx.x; T.nthreads = blockDim.x; T.warp = T.tid >> 5; T.lane = T.tid & 31;
+    T.nwarps = T.nthreads >> 5; T.lanes = 32;
+    return T;
+}
+VPK_DEV void team_sync() { __syncthreads(); }
+VPK_DEV double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+VPK_DEV int warp_sum_i(int v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+VPK_DEV int warp_max_i(int v) {
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+VPK_DEV long long warp_sum_ll(long long v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+VPK_DEV bool warp_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+// max that propagates NaN like numpy.max
+VPK_DEV double warp_max_nanprop(double v) {
+    for (int o = 16; o > 0; o >>= 1) {
+        double t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = (isnan(v) || isnan(t)) ? nan("") : (t > v ? t : v);
+    }
+    return v;
+}
+#else
+inline Team make_team() { return Team{0, 1, 0, 0, 1, 1}; }
+inline void team_sync() {}
+inline double warp_sum(double v) { return v; }
+inline int warp_sum_i(int v) { return v; }
+inline int warp_max_i(int v) { return v; }
+inline long long warp_sum_ll(long long v) { return v; }
+inline bool warp_any(bool p) { return p; }
+inline double warp_max_nanprop(double v) { return v; }
+#endif
+
+VPK_DEV double nanmax(double a, double b) { return (isnan(a) || isnan(b)) ? nan("") : (b > a ? b : a); }
+VPK_DEV double sign_np(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : 0.0); }   // numpy.sign
+VPK_DEV int imin(int a, int b) { return a < b ? a : b; }
+
+// ---------------------------------------------------------------------------
+// per-slot state (global memory; POST works on a shared-memory copy)
+// ---------------------------------------------------------------------------
+struct EmSlot {
+    int32_t img, N, base, phase, iter, M, vsel, run_e, run_w, done, status, iters_out;
+    int32_t merge_j, merge_k, after_merge, vidx, npdf, pad0;
+    double merge_thresh, sigma_prior;
+    unsigned long long ws_off;             // doubles from the workspace base
+    double cur[kMaxM][3], nxt[kMaxM][3], s[kMaxM];
+    // constants of the E-step on the selected VP set (prepare_estep)
+    double pv[kMaxM], vx[kMaxM], vy[kMaxM], two_s[kMaxM], coef[kMaxM];
+    double cw[kMaxM];
+    int32_t cnt[kMaxM];
+    double pdf_a[kMaxComp], pdf_b[kMaxComp], pdf_w[kMaxComp];
+};
+
+struct EmOut {
+    int32_t* status; int32_t* n_vp; int32_t* iterations;
+    double* vp; double* sigma; int32_t* counts; double* counts_weighted;
+    int32_t* vp_assoc; double* decision_metric;
+};
+
+// per-image view of the slot workspace
+struct Img {
+    int N;
+    const double* lp;      // (N,4) segments (input)
+    double* lsim;          // slab-major similarity matrix: element (j,k) at lsim_index(N,j,k)
+    double* ln;            // (N,3) unit lines
+    double* lweight;       // (N)
+    double* colsum;        // (N)
+    double* langle;        // (N)
+    int* assoc;            // (N)
+    double* lvsq;          // (kMaxM,N)  -- lvsq|pvl|w|wt are contiguous: split scratch
+    double* pvl;           // (kMaxM,N)
+    double* w;             // (kMaxM,N)
+    double* wt;            // (kMaxM/kMP, N, kMP): pvl*lweight, the A operand of the W kernel
+    size_t scratch_cap;    // doubles available from lvsq on
+};
+
+VPK_HD size_t lsim_doubles(int N) { return (size_t)((N + kTK - 1) / kTK) * kTK * (size_t)N; }
+VPK_HD size_t lsim_index(int N, int j, int k) { return ((size_t)(k / kTK) * N + j) * kTK + (k % kTK); }
+VPK_HD size_t wt_index(int N, int n, int m) { return ((size_t)(m / kMP) * N + n) * kMP + (m % kMP); }
+VPK_HD size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+VPK_HD size_t slot_doubles(int N) {
+    size_t n = (size_t)N;
+    return align16(lsim_doubles(N)) + align16(3 * n) + 3 * align16(n) + align16((n + 1) / 2 + 1) + 4 * align16((size_t)kMaxM * n) + 16;
+}
+
+VPK_DEV Img make_img(int N, double* ws, const double* lp) {
+    Img im;
+    size_t n = (size_t)N;
+    im.N = N; im.lp = lp;
+    double* p = ws;
+    im.lsim = p; p += align16(lsim_doubles(N));
+    im.ln = p; p += align16(3 * n);
+    im.lweight = p; p += align16(n);
+    im.colsum = p; p += align16(n);
+    im.langle = p; p += align16(n);
+    im.assoc = reinterpret_cast<int*>(p); p += align16((n + 1) / 2 + 1);
+    im.lvsq = p; p += align16((size_t)kMaxM * n);
+    im.pvl = p; p += align16((size_t)kMaxM * n);
+    im.w = p; p += align16((size_t)kMaxM * n);
+    im.wt = p; p += align16((size_t)kMaxM * n);
+    im.scratch_cap = 4 * align16((size_t)kMaxM * n);
+    return im;
+}
+
+// ---------------------------------------------------------------------------
+// segment-pair geometry (vp_localisation.py:700-762)
+// ---------------------------------------------------------------------------
+struct Seg { double x1, y1, x2, y2; };
+VPK_DEV Seg load_seg(const double* lp, int n) {
+    const double* p = lp + 4 * (size_t)n;
+    Seg s; s.x1 = p[0]; s.y1 = p[1]; s.x2 = p[2]; s.y2 = p[3];
+    return s;
+}
+// line_segment_point_distance (:743-758), squared; note the squared *norm* of :747
+VPK_DEV double psd2(const Seg& s, double px, double py) {
+    double dx = s.x2 - s.x1, dy = s.y2 - s.y1;
+    double nrm = sqrt(dx * dx + dy * dy);
+    double param = ((px - s.x1) * dx + (py - s.y1) * dy) / (nrm * nrm);
+    double cx, cy;
+    if (param < 0) { cx = s.x1; cy = s.y1; }
+    else if (param > 1) { cx = s.x2; cy = s.y2; }
+    else { cx = s.x1 + param * dx; cy = s.y1 + param * dy; }
+    double ex = cx - px, ey = cy - py;
+    return ex * ex + ey * ey;
+}
+// line_distance_closest (:727-740).  sqrt is monotone and correctly rounded, so the minimum of
+// the four distances is the root of the minimum of the four squared distances, bit for bit.
+VPK_DEV double seg_distance(const Seg& a, const Seg& b) {
+    double d1 = psd2(a, b.x1, b.y1), d2 = psd2(a, b.x2, b.y2), d4 = psd2(b, a.x1, a.y1), d5 = psd2(b, a.x2, a.y2);
+    return sqrt(fmin(fmin(d1, d2), fmin(d4, d5)));
+}
+VPK_DEV double seg_len(const Seg& a) {
+    double dx = a.x1 - a.x2, dy = a.y1 - a.y2;
+    return sqrt(dx * dx + dy * dy);
+}
+// lines_points_cosangle (:715-724)
+VPK_DEV double cosangle(const Seg& a, const Seg& b, double f) {
+    double v1x = a.x1 - a.x2, v1y = a.y1 - a.y2, v2x = b.x1 - b.x2, v2y = b.y1 - b.y2;
+    double c = fabs((v1x * v2x + v1y * v2y) / (sqrt(v1x * v1x + v1y * v1y) * sqrt(v2x * v2x + v2y * v2y)));
+    double dphi = fabs(acos(fmin(fmax(c, -1.0), 1.0)));
+    if (isnan(c)) dphi = c;
+    return cos(fmin(fmax(f * dphi, -0.5 * kPi), 0.5 * kPi));
+}
+// lines_proximity (:708-712), sigma = 1
+VPK_DEV double proximity(const Seg& a, const Seg& b, double d) {
+    double sg = fmin(seg_len(a), seg_len(b));
+    return exp(-(d * d) / (2 * sg * sg));
+}
+// lines_similarity (:700-705)
+VPK_DEV double similarity(const Seg& a, const Seg& b, double d) { return cosangle(a, b, 9.0) * proximity(a, b, d); }
+
+// E4 tail (vp_localisation.py:50-72, :230-233): line score from the k1 nearest segments
+// cj/cd (ascending distance, ties by index; the line itself enters with distance 4, :82).
+VPK_DEVFN double rate_line(const double* lp, int i, const int* cj, const double* cd, int cnt, int N) {
+    const int k2 = imin(4, N);
+    const Seg si = load_seg(lp, i);
+    double c[kK1], px[kK1];
+    for (int q = 0; q < cnt; ++q) {
+        Seg sj = load_seg(lp, cj[q]);
+        double cc = cosangle(si, sj, 9.0);
+        double dtrue = (cj[q] == i) ? seg_distance(si, sj) : cd[q];       // :65 recomputes the true distance
+        px[q] = proximity(si, sj, dtrue);
+        c[q] = isnan(cc) ? -INFINITY : cc;
+    }
+    // the k2 largest cosangles, descending; argsort()[::-1] puts the later of equal values first (:57-59)
+    double score = 0.0;
+    for (int r = 0; r < k2 && r < cnt; ++r) {
+        int who = 0;
+        for (int q = 1; q < cnt; ++q)
+            if (c[q] >= c[who]) who = q;
+        score += px[who] * c[who];
+        c[who] = -INFINITY;
+    }
+    score /= (double)k2;
+    double ls = fmin(fmax(score, 0.2), 1.0);      // :231
+    if (isnan(score)) ls = score;
+    return seg_len(si) * ls;                      // :232-233
+}
+
+// insert (d, j) into an ascending candidate list of capacity kK1 (ties: smaller j first).
+// stride: element q of the list lives at kd[q * stride], kj[q * stride].
+VPK_DEV void knn_insert(double* kd, int* kj, int stride, int& cnt, double d, int j) {
+    if (isnan(d)) d = INFINITY;
+    int pos;
+    if (cnt < kK1) pos = cnt++;
+    else {
+        double ld = kd[(kK1 - 1) * stride];
+        int lj = kj[(kK1 - 1) * stride];
+        if (!(d < ld || (d == ld && j < lj))) return;
+        pos = kK1 - 1;
+    }
+    while (pos > 0) {
+        double pd = kd[(pos - 1) * stride];
+        int pj = kj[(pos - 1) * stride];
+        if (!(pd > d || (pd == d && pj > j))) break;
+        kd[pos * stride] = pd; kj[pos * stride] = pj;
+        --pos;
+    }
+    kd[pos * stride] = d; kj[pos * stride] = j;
+}
+
+// ---------------------------------------------------------------------------
+// eigenvector of the smallest eigenvalue of the symmetric 3x3 matrix
+// [g0 g1 g2; g1 g3 g4; g2 g4 g5] (cyclic Jacobi, float64).  false if not finite.
+// Replaces SVD(diag(w) l) of calc_new_vanishing_point (vp_localisation.py:453-479).
+// ---------------------------------------------------------------------------
+VPK_DEVFN bool smallest_eigvec3(const double g[6], double out[3]) {
+    double tr = g[0] + g[3] + g[5];
+    if (!(tr > 0.0) || isinf(tr)) return false;
+    double sc = 1.0 / tr;
+    double a[3][3] = {{g[0] * sc, g[1] * sc, g[2] * sc}, {g[1] * sc, g[3] * sc, g[4] * sc}, {g[2] * sc, g[4] * sc, g[5] * sc}};
+    double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            if (isnan(a[i][j])) return false;
+    for (int sweep = 0; sweep < 24; ++sweep) {
+        double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+        if (off < 1e-40) break;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+            double apq = a[p][q];
+            if (apq == 0.0) continue;
+            double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
+            double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            if (isinf(theta)) t = 0.0;
+            double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+            double app = a[p][p], aqq = a[q][q];
+            a[p][p] = app - t * apq;
+            a[q][q] = aqq + t * apq;
+            a[p][q] = a[q][p] = 0.0;
+            const int r = 3 - p - q;
+            double arp = a[r][p], arq = a[r][q];
+            a[r][p] = a[p][r] = c * arp - sn * arq;
+            a[r][q] = a[q][r] = sn * arp + c * arq;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                double vkp = v[k][p], vkq = v[k][q];
+                v[k][p] = c * vkp - sn * vkq;
+                v[k][q] = sn * vkp + c * vkq;
+            }
+        }
+    }
+    int m = 0;
+    if (a[1][1] < a[m][m]) m = 1;
+    if (a[2][2] < a[m][m]) m = 2;
+    double x = v[0][m], y = v[1][m], z = v[2][m];
+    double n = sqrt(x * x + y * y + z * z);
+    if (!(n > 0.0)) return false;
+    out[0] = x / n; out[1] = y / n; out[2] = z / n;
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// scratch of the per-slot kernels (shared memory on the device)
+// ---------------------------------------------------------------------------
+struct PostScratch {
+    double redv[kPostThreads];
+    int redi[kPostThreads], redj[kPostThreads];
+    double ang[kMaxM], err[kMaxM], nv[kMaxM][3];
+    int ok[kMaxM], rem[kMaxM];
+    int ia, ib, flag;
+    double da;
+};
+
+struct InitScratch {
+    double resp[kCells];
+    double cand[kCells][3];
+    int keep[kCells], ismax[kCells], has[kCells];
+};
+
+// ---------------------------------------------------------------------------
+// per-line constants: unit lines (:186/:226), segment angles (:765-776)
+// ---------------------------------------------------------------------------
+VPK_DEVFN void line_constants(const Img& im, const double* lines, const Team& T) {
+    const int N = im.N;
+    for (int n = T.tid; n < N; n += T.nthreads) {
+        const double* l = lines + 3 * (size_t)n;
+        double a = l[0], bb = l[1], c = l[2];
+        double nr = sqrt(a * a + bb * bb + c * c);
+        a /= nr; bb /= nr; c /= nr;
+        nr = sqrt(a * a + bb * bb + c * c);               // the reference normalises twice
+        im.ln[3 * (size_t)n] = a / nr; im.ln[3 * (size_t)n + 1] = bb / nr; im.ln[3 * (size_t)n + 2] = c / nr;
+        Seg sg = load_seg(im.lp, n);
+        double vx = sg.x1 - sg.x2, vy = sg.y1 - sg.y2;
+        vx = vx / sqrt(vx * vx + vy * vy);
+        double phi = fabs(acos(fmin(fmax(vx, -1.0), 1.0)));
+        im.langle[n] = phi > 0.5 * kPi ? kPi - phi : phi;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// E0/E1/E2: prior mixture and initial VPs.  resp: this image's (20,20) response
+// already staged in sc.resp.  Sets st.npdf/pdf_*/sigma_prior and, unless
+// have_init, st.cur / st.M.
+// ---------------------------------------------------------------------------
+VPK_DEVFN void init_prior_and_vps(EmSlot& st, InitScratch& sc, const uint8_t* img, int S, int num_init_vp,
+                                  bool have_init, const Team& T) {
+    const int G = VPK_GRID;
+    // --- E2 pdf_params (probability_functions.py:62-96): top-100 cells
+    for (int c = T.tid; c < kCells; c += T.nthreads) {
+        double v = sc.resp[c];
+        int rank = 0;
+        for (int o = 0; o < kCells; ++o) {
+            double u = sc.resp[o];
+            rank += (u > v) || (u == v && o > c);
+        }
+        sc.keep[c] = rank < kMaxComp;
+    }
+    team_sync();
+    if (T.tid == 0) {
+        double sum = 0.0;
+        for (int c = 0; c < kCells; ++c) if (sc.keep[c]) sum += sc.resp[c];
+        double sigma = kPi / (1.282 * G);
+        st.sigma_prior = sigma;
+        int n = 0;
+        for (int c = 0; c < kCells; ++c) {
+            if (!sc.keep[c]) continue;
+            double w = sc.resp[c] / sum / (2 * kPi * sigma * sigma);
+            if (!(w > 0)) continue;                    // calc_pdf skips weights <= 0 (:21)
+            int a = c % G, bb = c / G;
+            // numpy.linspace(-(G-1)/G*pi/2, (G-1)/G*pi/2, G)
+            double lo = -(G - 1.0) / G * kPi / 2, hi = (G - 1.0) / G * kPi / 2, stp = (hi - lo) / (G - 1);
+            st.pdf_a[n] = a == G - 1 ? hi : a * stp + lo;
+            st.pdf_b[n] = bb == G - 1 ? hi : bb * stp + lo;
+            st.pdf_w[n] = w;
+            ++n;
+        }
+        st.npdf = n;
+    }
+    team_sync();
+    if (have_init) return;
+    // --- E0 find_maxima (vp_localisation.py:13-31, border quirk included)
+    for (int c = T.tid; c < kCells; c += T.nthreads) {
+        int a = c % G, bb = c / G;
+        double vm = sc.resp[c];
+        double vu = a + 1 < G ? sc.resp[bb * G + a + 1] : 0.0;
+        double vd = a - 1 > 0 ? sc.resp[bb * G + a - 1] : 0.0;
+        double vl = bb - 1 > 0 ? sc.resp[(bb - 1) * G + a] : 0.0;
+        double vr = bb + 1 < G ? sc.resp[(bb + 1) * G + a] : 0.0;
+        sc.ismax[c] = (vm > vu && vm > vd && vm > vl && vm > vr) ? 1 : 0;
+    }
+    team_sync();
+    // keep the num_init_vp strongest maxima (:121-126)
+    for (int c = T.tid; c < kCells; c += T.nthreads) {
+        if (!sc.ismax[c]) { sc.keep[c] = 0; continue; }
+        double v = sc.resp[c];
+        int rank = 0;
+        for (int o = 0; o < kCells; ++o)
+            if (sc.ismax[o]) { double u = sc.resp[o]; rank += (u > v) || (u == v && o > c); }
+        sc.keep[c] = rank < num_init_vp;
+    }
+    team_sync();
+    // --- E1: per kept cell, mean index of the brightest pixels of the flipped sphere slice
+    for (int c = T.warp; c < kCells; c += T.nwarps) {
+        if (!sc.keep[c]) { if (T.lane == 0) sc.has[c] = 0; continue; }
+        int ra = c / G, rb = c % G;      // ra: row of the response (beta), rb: column (alpha)
+        int r0 = ra * S / G, r1 = (ra + 1) * S / G, c0 = rb * S / G, c1 = (rb + 1) * S / G;
+        int w = c1 - c0, npx = (r1 - r0) * w;
+        int mx = 0;
+        for (int e = T.lane; e < npx; e += T.lanes) {
+            int r = r0 + e / w, cc = c0 + e % w;
+            int px = (int)img[(size_t)(S - 1 - r) * S + cc];      // flipped vertically (:114)
+            mx = px > mx ? px : mx;
+        }
+        mx = warp_max_i(mx);
+        long long sr = 0, scol = 0;
+        int cnt = 0;
+        if (mx > 0)
+            for (int e = T.lane; e < npx; e += T.lanes) {
+                int r = e / w, cc = e % w;
+                if ((int)img[(size_t)(S - 1 - (r0 + r)) * S + c0 + cc] == mx) { sr += r; scol += cc; ++cnt; }
+            }
+        sr = warp_sum_ll(sr); scol = warp_sum_ll(scol); cnt = warp_sum_i(cnt);
+        if (T.lane == 0) {
+            sc.has[c] = cnt > 0;
+            if (cnt > 0) {
+                double idx0 = (double)scol / (double)cnt + c0;   // :158
+                double idx1 = (double)sr / (double)cnt + r0;     // :157
+                double alpha = (idx0 - 0.5 * S + 0.5) * kPi / S; // index_to_angle
+                double beta = (idx1 - 0.5 * S + 0.5) * kPi / S;
+                double x = sin(alpha) * cos(beta), y = sin(beta), z = cos(alpha) * cos(beta);
+                double sg = sign_np(z);                          // angle_to_point :48
+                sc.cand[c][0] = x * sg; sc.cand[c][1] = y * sg; sc.cand[c][2] = z * sg;
+            }
+        }
+    }
+    team_sync();
+    if (T.tid == 0) {
+        int M = 0;
+        for (int c = 0; c < kCells && M < kMaxM; ++c)
+            if (sc.keep[c] && sc.has[c]) {
+                st.cur[M][0] = sc.cand[c][0]; st.cur[M][1] = sc.cand[c][1]; st.cur[M][2] = sc.cand[c][2];
+                ++M;
+            }
+        st.M = M;
+    }
+    team_sync();
+}
+
+// ---------------------------------------------------------------------------
+// E5 part 1: constants of the E-step for the VP set `v` (prior at the VP angles:
+// calc_angles probability_functions.py:252-259 + calc_pdf :8-40; the in-place
+// clamp of s in calc_plv :139).
+// ---------------------------------------------------------------------------
+VPK_DEVFN void prepare_estep(EmSlot& st, const double (*v)[3], const Team& T) {
+    const int M = st.M;
+    for (int m = T.warp; m < M; m += T.nwarps) {
+        double beta = asin(v[m][1]);
+        double inner = v[m][0] / cos(beta);
+        inner = fmax(fmin(inner, 1.0), -1.0);
+        if (isnan(v[m][0] / cos(beta))) inner = nan("");
+        double x = asin(inner), y = beta;
+        const double k = -0.5 / (st.sigma_prior * st.sigma_prior);
+        double acc = 0.0;
+        for (int n = T.lane; n < st.npdf; n += T.lanes) {
+            double mx = st.pdf_a[n], my = st.pdf_b[n];
+            double d1 = (x - mx) * (x - mx) + (y - my) * (y - my);
+            double d2 = (x - mx + kPi) * (x - mx + kPi) + (y + my) * (y + my);
+            double d3 = (x - mx - kPi) * (x - mx - kPi) + (y + my) * (y + my);
+            double d4 = (x + mx) * (x + mx) + (y - my - kPi) * (y - my - kPi);
+            double p = exp(d1 * k) + exp(d2 * k) + exp(d3 * k) + exp(d4 * k) + exp(d4 * k);   // 4th == 5th (:25-26)
+            acc += p * st.pdf_w[n];
+        }
+        acc = warp_sum(acc);
+        if (T.lane == 0) {
+            st.pv[m] = acc;
+            st.vx[m] = v[m][0] / v[m][2];
+            st.vy[m] = v[m][1] / v[m][2];
+            double sm = st.s[m] > 1e-200 ? st.s[m] : 1e-200;    // calc_plv mutates s (:139)
+            if (isnan(st.s[m])) sm = 1e-200;
+            st.s[m] = sm;
+            st.two_s[m] = 2.0 * sm;
+            st.coef[m] = 1.0 / sqrt(2.0 * kPi * sm);
+        }
+    }
+    team_sync();
+}
+
+// E5 part 2 for line n (probability_functions.py:99-147): lvsq, p(v|l), and the
+// W-kernel operand wt = p(v|l) * lweight.  c: pv/vx/vy/two_s/coef of the slot.
+VPK_DEV void estep_line(const Img& im, int M, const double* pv, const double* vx, const double* vy, const double* two_s,
+                        const double* coef, int n) {
+    const int N = im.N;
+    Seg sg = load_seg(im.lp, n);
+    double mx = 0.5 * (sg.x1 + sg.x2), my = 0.5 * (sg.y1 + sg.y2);
+    double bx = sg.x1 - sg.x2, by = sg.y1 - sg.y2;
+    double nb = sqrt(bx * bx + by * by);
+    double pl = 0.0;
+    for (int m = 0; m < M; ++m) {
+        double ax = mx - vx[m], ay = my - vy[m];
+        double c = (ax * bx + ay * by) / (sqrt(ax * ax + ay * ay) * nb);
+        double q = 1.0 - fabs(c);
+        double lvsq = q * q;                                            // calc_lvsq_angle (:174)
+        double plv = exp(-(lvsq / two_s[m])) * coef[m];                 // calc_plv (:140-145)
+        im.lvsq[(size_t)m * N + n] = lvsq;
+        im.pvl[(size_t)m * N + n] = plv;
+        pl += plv * pv[m];
+    }
+    if (pl < 1e-12) pl = 1e-12;                                         // :117 (NaN stays NaN)
+    const double lw = im.lweight[n];
+    const int mpad = ((M + kMP - 1) / kMP) * kMP;
+    for (int m = 0; m < mpad; ++m) {
+        double x = 0.0;
+        if (m < M) {
+            x = im.pvl[(size_t)m * N + n] * pv[m] / pl;                 // calc_pvl (:128)
+            im.pvl[(size_t)m * N + n] = x;
+            x *= lw;                                                    // weight_matrix :517
+        }
+        im.wt[wt_index(N, n, m)] = x;
+    }
+}
+
+// E6 epilogue (vp_localisation.py:519-523): acc = sum_j wt[j,m] * lsim[j,k]
+VPK_DEV double wmat_finish(double wt_mk, double lw_k, double colsum_k, double acc, double bias) {
+    return (wt_mk + bias * lw_k * acc) / (1 + bias * lw_k * colsum_k);
+}
+
+// ---------------------------------------------------------------------------
+// reductions over the lines used by POST
+// ---------------------------------------------------------------------------
+// assoc[n] = argmax_m w[m,n] (first maximum, numpy.argmax; NaN counts as max)
+VPK_DEVFN void argmax_assoc(const Img& im, int M, const Team& T) {
+    const int N = im.N;
+    for (int n = T.tid; n < N; n += T.nthreads) {
+        int best = 0;
+        double bv = M > 0 ? im.w[n] : 0.0;
+        for (int m = 1; m < M; ++m) {
+            double x = im.w[(size_t)m * N + n];
+            if (isnan(bv)) break;
+            if (x > bv || isnan(x)) { bv = x; best = m; }
+        }
+        im.assoc[n] = best;
+    }
+    team_sync();
+}
+
+// E9: calc_vp_line_counts (vp_localisation.py:482-512).  lvsq must have been
+// computed (E-step) for the same VP set that is being counted.
+VPK_DEVFN void line_counts(const Img& im, EmSlot& st, double thresh, const Team& T) {
+    const int M = st.M, N = im.N;
+    argmax_assoc(im, M, T);
+    for (int n = T.tid; n < N; n += T.nthreads) {
+        int m = im.assoc[n];
+        double dist = im.lvsq[(size_t)m * N + n];
+        if (dist > thresh * sqrt(st.s[m]) || im.lweight[n] == 0.0) im.assoc[n] = -1;
+    }
+    team_sync();
+    for (int m = T.warp; m < M; m += T.nwarps) {
+        int c = 0;
+        double cw = 0.0;
+        for (int n = T.lane; n < N; n += T.lanes)
+            if (im.assoc[n] == m) { ++c; cw += im.lweight[n]; }
+        c = warp_sum_i(c);
+        cw = warp_sum(cw);
+        if (T.lane == 0) { st.cnt[m] = c; st.cw[m] = cw; }
+    }
+    team_sync();
+}
+
+// E7 for one VP by one warp: smallest eigenvector of sum (w/max w)^2 l l^T over
+// the selected lines.  sel < 0: all lines; sel >= 0: only lines with assoc == sel
+// (final refit).  wrow2: optional second weight row added to the first (merge).
+VPK_DEVFN bool refit_vp(const Img& im, const double* wrow, const double* wrow2, int sel, double out[3], const Team& T) {
+    const int N = im.N;
+    double mx = -INFINITY;
+    bool any = false;
+    for (int n = T.lane; n < N; n += T.lanes) {
+        if (sel >= 0 && im.assoc[n] != sel) continue;
+        double x = wrow[n] + (wrow2 ? wrow2[n] : 0.0);
+        any = true;
+        mx = nanmax(mx, x);
+    }
+    mx = warp_max_nanprop(mx);
+    any = warp_any(any);
+    if (!any || mx == 0.0 || isnan(mx) || isinf(mx)) return false;      // :456-460 / LinAlgError
+    double g[6] = {0, 0, 0, 0, 0, 0};
+    int rows = 0, only = -1;
+    for (int n = T.lane; n < N; n += T.lanes) {
+        if (sel >= 0 && im.assoc[n] != sel) continue;
+        double x = (wrow[n] + (wrow2 ? wrow2[n] : 0.0)) / mx;
+        double a = x * im.ln[3 * (size_t)n], b = x * im.ln[3 * (size_t)n + 1], c = x * im.ln[3 * (size_t)n + 2];
+        g[0] += a * a; g[1] += a * b; g[2] += a * c; g[3] += b * b; g[4] += b * c; g[5] += c * c;
+        ++rows; only = n;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) g[k] = warp_sum(g[k]);
+    rows = warp_sum_i(rows);
+    only = warp_max_i(only);
+    double e[3];
+    bool okv;
+    if (rows == 1) {
+        // A single 1x3 row has a 2-D null space; LAPACK's full SVD (what numpy.linalg.svd runs,
+        // vp_localisation.py:466) completes V with the Householder reflector of dgelqf/dlarfg:
+        // V[:,2] = row 3 of H = I - tau v v^T, v = (1, a2/(a1-beta), a3/(a1-beta)).
+        double x = (wrow[only] + (wrow2 ? wrow2[only] : 0.0)) / mx;
+        double a1 = x * im.ln[3 * (size_t)only], a2 = x * im.ln[3 * (size_t)only + 1], a3 = x * im.ln[3 * (size_t)only + 2];
+        double nrm = sqrt(a1 * a1 + a2 * a2 + a3 * a3);
+        double beta = -copysign(nrm, a1);
+        double tau = (beta - a1) / beta;
+        double v2 = a2 / (a1 - beta), v3 = a3 / (a1 - beta);
+        e[0] = -tau * v3; e[1] = -tau * v3 * v2; e[2] = 1.0 - tau * v3 * v3;
+        double n2 = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+        okv = n2 > 0.0 && !isnan(n2);
+        if (okv) { e[0] /= n2; e[1] /= n2; e[2] /= n2; }
+    } else {
+        okv = smallest_eigvec3(g, e);
+    }
+    if (!okv) return false;
+    double sg = sign_np(e[2]);                                           // :474
+    out[0] = e[0] * sg; out[1] = e[1] * sg; out[2] = e[2] * sg;
+    return true;
+}
+
+// s = exp(log(sum lvsq*pvl) - log(sum pvl))   (vp_localisation.py:301-304), one warp
+VPK_DEVFN double variance_update(const Img& im, int m, int m2, const Team& T) {
+    const int N = im.N;
+    double num = 0.0, den = 0.0;
+    for (int n = T.lane; n < N; n += T.lanes) {
+        double p = im.pvl[(size_t)m * N + n];
+        double q = im.lvsq[(size_t)m * N + n];
+        if (m2 >= 0) { p += im.pvl[(size_t)m2 * N + n]; q = 0.5 * (im.lvsq[(size_t)m2 * N + n] + q); }   // merge (:663-664)
+        num += q * p;
+        den += p;
+    }
+    num = warp_sum(num);
+    den = warp_sum(den);
+    return exp(log(num) - log(den));
+}
+
+// remove the VPs flagged in rem[] from cur / nxt / s (numpy.delete along the VP axis)
+VPK_DEVFN void compact_vps(EmSlot& st, const int* rem, const Team& T) {
+    team_sync();
+    if (T.tid == 0) {
+        int k = 0;
+        for (int m = 0; m < st.M; ++m) {
+            if (rem[m]) continue;
+            if (k != m) {
+                for (int c = 0; c < 3; ++c) { st.cur[k][c] = st.cur[m][c]; st.nxt[k][c] = st.nxt[m][c]; }
+                st.s[k] = st.s[m];
+            }
+            ++k;
+        }
+        st.M = k;
+    }
+    team_sync();
+}
+
+// ---------------------------------------------------------------------------
+// E11: split_best_vp (vp_localisation.py:527-630)
+// ---------------------------------------------------------------------------
+// UPGMA down to two clusters on the n x n matrix D (what scikit-learn's
+// AgglomerativeClustering(linkage='average', n_clusters=2) computes on a
+// complete connectivity graph); labels follow _hc_cut: label 0 = the root's
+// child with the larger node id.
+VPK_DEVFN void average_linkage_two(double* D, int n, int* rep, int* nodeid, double* csize, PostScratch& sc, const Team& T) {
+    const int tid = T.tid, NT = T.nthreads;
+    for (int i = tid; i < n; i += NT) { rep[i] = i; nodeid[i] = i; csize[i] = 1.0; }
+    team_sync();
+    for (int step = 0; step < n - 2; ++step) {
+        // global minimum over active pairs a < b, lexicographic tie-break
+        double bd = INFINITY;
+        int ba = -1, bb = -1;
+        for (int a = tid; a < n; a += NT) {
+            if (nodeid[a] < 0) continue;
+            const double* row = D + (size_t)a * n;
+            for (int b = a + 1; b < n; ++b) {
+                if (nodeid[b] < 0) continue;
+                double d = row[b];
+                if (d < bd) { bd = d; ba = a; bb = b; }
+            }
+        }
+        sc.redv[tid] = bd; sc.redi[tid] = ba; sc.redj[tid] = bb;
+        team_sync();
+        for (int o = NT / 2; o > 0; o >>= 1) {
+            if (tid < o) {
+                double od = sc.redv[tid + o];
+                int oa = sc.redi[tid + o], ob = sc.redj[tid + o];
+                bool take = oa >= 0 && (sc.redi[tid] < 0 || od < sc.redv[tid] ||
+                                        (od == sc.redv[tid] && (oa < sc.redi[tid] || (oa == sc.redi[tid] && ob < sc.redj[tid]))));
+                if (take) { sc.redv[tid] = od; sc.redi[tid] = oa; sc.redj[tid] = ob; }
+            }
+            team_sync();
+        }
+        const int a = sc.redi[0], b = sc.redj[0];
+        team_sync();
+        if (a < 0) break;
+        const double na = csize[a], nb = csize[b];
+        for (int c = tid; c < n; c += NT) {
+            if (c == a || c == b || nodeid[c] < 0) continue;
+            double dn = (na * D[(size_t)a * n + c] + nb * D[(size_t)b * n + c]) / (na + nb);   // average_merge
+            D[(size_t)a * n + c] = dn;
+            D[(size_t)c * n + a] = dn;
+        }
+        for (int i = tid; i < n; i += NT)
+            if (rep[i] == b) rep[i] = a;
+        team_sync();
+        if (tid == 0) { csize[a] = na + nb; nodeid[a] = n + step; nodeid[b] = -1; }
+        team_sync();
+    }
+    // the two survivors; label 0 = larger node id
+    if (tid == 0) {
+        int c0 = -1, c1 = -1;
+        for (int i = 0; i < n; ++i)
+            if (nodeid[i] >= 0) { if (c0 < 0) c0 = i; else c1 = i; }
+        if (c1 >= 0 && nodeid[c1] > nodeid[c0]) { int t = c0; c0 = c1; c1 = t; }
+        sc.ia = c0; sc.ib = c1;
+    }
+    team_sync();
+    const int c0 = sc.ia;
+    for (int i = tid; i < n; i += NT) rep[i] = (rep[i] == c0) ? 0 : 1;
+    team_sync();
+}
+
+// Returns -1 if nothing was touched (no VP qualifies), 0 if the scratch (E/W results) was
+// overwritten but the hypothesis set is unchanged, 1 if it changed.  big/big_cap: scratch used when the
+// clustering of the chosen VP does not fit the slot's own scratch (nullptr: skip).
+VPK_DEVFN int split_best_vp(const Img& im, EmSlot& st, PostScratch& sc, double min_diff, double* big, size_t big_cap,
+                            int* big_lock, const Team& T) {
+    const int M = st.M, N = im.N, tid = T.tid;
+    argmax_assoc(im, M, T);
+    // global maximum of w (weightMatrix.max(), :539) only decides the sign of the greedy entries
+    double lm = -INFINITY;
+    for (size_t e = tid; e < (size_t)M * N; e += T.nthreads) lm = nanmax(lm, im.w[e]);
+    lm = warp_max_nanprop(lm);
+    if (T.lane == 0) sc.redv[T.warp] = lm;
+    team_sync();
+    if (tid == 0) {
+        double g = sc.redv[0];
+        for (int k = 1; k < T.nwarps; ++k) g = nanmax(g, sc.redv[k]);
+        sc.da = g;
+    }
+    team_sync();
+    const double wmax = sc.da;
+    // std of the segment angles of the lines greedily assigned to each VP (:541-544), lines per VP
+    for (int m = T.warp; m < M; m += T.nwarps) {
+        double sum = 0.0;
+        int c = 0, call = 0;
+        for (int n = T.lane; n < N; n += T.lanes) {
+            if (im.assoc[n] != m) continue;
+            ++call;
+            if ((im.w[(size_t)m * N + n] / wmax) > 0) { sum += im.langle[n]; ++c; }
+        }
+        sum = warp_sum(sum);
+        c = warp_sum_i(c);
+        call = warp_sum_i(call);
+        double mean = sum / c, var = 0.0;
+        for (int n = T.lane; n < N; n += T.lanes)
+            if (im.assoc[n] == m && (im.w[(size_t)m * N + n] / wmax) > 0) { double d = im.langle[n] - mean; var += d * d; }
+        var = warp_sum(var);
+        if (T.lane == 0) { sc.ang[m] = c > 0 ? sqrt(var / c) : nan(""); st.cnt[m] = call; }
+    }
+    team_sync();
+    if (tid == 0) {
+        // argsort(std)[::-1]: ascending, NaN last, stable; then reversed (:546-547)
+        int ord[kMaxM];
+        for (int m = 0; m < M; ++m) ord[m] = m;
+        for (int i = 1; i < M; ++i) {
+            int x = ord[i];
+            double kx = isnan(sc.ang[x]) ? INFINITY : sc.ang[x];
+            bool nx = isnan(sc.ang[x]);
+            int p = i;
+            while (p > 0) {
+                int y = ord[p - 1];
+                double ky = isnan(sc.ang[y]) ? INFINITY : sc.ang[y];
+                bool ny = isnan(sc.ang[y]);
+                bool greater = (ny && !nx) || (!ny && !nx && ky > kx);
+                if (!greater) break;
+                ord[p] = y; --p;
+            }
+            ord[p] = x;
+        }
+        int worst = -1;
+        for (int m = 0; m < M; ++m) {
+            int cand = ord[M - 1 - m];
+            double px = st.cur[m][0] / st.cur[m][2], py = st.cur[m][1] / st.cur[m][2];     // row m, not cand (:557)
+            if (st.cnt[cand] > 8 && px > -1 && py > -1 && px < 1 && py < 1) { worst = cand; break; }
+        }
+        sc.ia = worst;
+    }
+    team_sync();
+    const int worst = sc.ia;
+    if (worst < 0) return -1;
+    const int nw = st.cnt[worst];
+    // scratch layout (doubles): D[nw*nw] | csize[nw] | ints: idx[nw] rep[nw] nodeid[nw]
+    size_t need = (size_t)nw * nw + nw + (3 * (size_t)nw + 1) / 2 + 4;
+    double* scratch = im.lvsq;
+    bool locked = false;
+    // the line -> VP association and the line weights live outside the scratch region; the E/W
+    // results in it are dead after this point (the next superstep recomputes them)
+    if (need > im.scratch_cap) {
+        if (!big || need > big_cap) return -1;           // cannot split: leave the hypothesis set unchanged
+        scratch = big;
+        locked = true;
+#if defined(__CUDACC__)
+        // one clustering at a time in the shared overflow buffer
+        if (tid == 0) { while (atomicCAS(big_lock, 0, 1) != 0) __nanosleep(200); __threadfence(); }
+        team_sync();
+#endif
+    }
+    double* D = scratch;
+    double* csize = D + (size_t)nw * nw;
+    int* idx = reinterpret_cast<int*>(csize + nw);
+    int* rep = idx + nw;
+    int* nodeid = rep + nw;
+    if (tid == 0) {
+        int k = 0;
+        for (int n = 0; n < N; ++n) if (im.assoc[n] == worst) idx[k++] = n;
+    }
+    team_sync();
+    for (size_t e = tid; e < (size_t)nw * nw; e += T.nthreads) {
+        int a = (int)(e / nw), b = (int)(e % nw);
+        double d = 0.0;
+        if (a != b) d = 1.0 - cosangle(load_seg(im.lp, idx[a]), load_seg(im.lp, idx[b]), 2.0);     // :572
+        D[e] = d;
+    }
+    team_sync();
+    average_linkage_two(D, nw, rep, nodeid, csize, sc, T);
+    // per cluster: smallest right-singular vector of the lweight-scaled lines (:580-602)
+    for (int c = T.warp; c < 2; c += T.nwarps) {
+        double g[6] = {0, 0, 0, 0, 0, 0};
+        int cnt = 0;
+        for (int q = T.lane; q < nw; q += T.lanes) {
+            if (rep[q] != c) continue;
+            int n = idx[q];
+            double lw = im.lweight[n];
+            double a = im.ln[3 * (size_t)n] * lw, b = im.ln[3 * (size_t)n + 1] * lw, cc = im.ln[3 * (size_t)n + 2] * lw;
+            g[0] += a * a; g[1] += a * b; g[2] += a * cc; g[3] += b * b; g[4] += b * cc; g[5] += cc * cc;
+            ++cnt;
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) g[k] = warp_sum(g[k]);
+        cnt = warp_sum_i(cnt);
+        double e[3] = {0, 0, 0};
+        bool okv = cnt >= 3 && smallest_eigvec3(g, e);
+        if (T.lane == 0) {
+            sc.ok[c] = okv;
+            double sg = e[2] < 0 ? -1.0 : 1.0;
+            sc.nv[c][0] = e[0] * sg; sc.nv[c][1] = e[1] * sg; sc.nv[c][2] = e[2] * sg;
+        }
+    }
+    team_sync();
+#if defined(__CUDACC__)
+    if (locked && tid == 0) { __threadfence(); atomicExch(big_lock, 0); }
+#else
+    (void)locked; (void)big_lock;
+#endif
+    if (tid == 0) {
+        sc.flag = 0;
+        if (sc.ok[0] && sc.ok[1]) {
+            double c = sc.nv[0][0] * sc.nv[1][0] + sc.nv[0][1] * sc.nv[1][1] + sc.nv[0][2] * sc.nv[1][2];
+            c = fmin(fmax(c, -1.0), 1.0);
+            double ang = fabs(acos(fmin(fmax(fabs(c), -1.0), 1.0)));
+            if (ang > min_diff && st.M < kMaxM) {
+                double stdd = st.s[worst] / 2;
+                for (int k = 0; k < 3; ++k) { st.cur[worst][k] = sc.nv[0][k]; st.cur[st.M][k] = sc.nv[1][k]; st.nxt[st.M][k] = 0.0; }
+                st.s[worst] = stdd;
+                st.s[st.M] = stdd;
+                st.M += 1;
+                sc.flag = 1;
+            }
+        }
+    }
+    team_sync();
+    return sc.flag != 0 ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------
+// result (vp_localisation.py:441-442)
+// ---------------------------------------------------------------------------
+VPK_DEVFN void write_result(const EmOut& out, const Img& im, EmSlot& st, int status, int iters, bool have_vps, const Team& T) {
+    const int N = im.N, b = st.img, base = st.base;
+    if (T.tid == 0) {
+        out.status[b] = status;
+        out.iterations[b] = iters;
+        out.n_vp[b] = have_vps ? st.M : 0;
+    }
+    for (int m = T.tid; m < kMaxM; m += T.nthreads) {
+        bool live = have_vps && m < st.M;
+        for (int c = 0; c < 3; ++c) out.vp[((size_t)b * kMaxM + m) * 3 + c] = live ? st.nxt[m][c] : 0.0;
+        out.sigma[(size_t)b * kMaxM + m] = live ? st.s[m] : 0.0;
+        out.counts[(size_t)b * kMaxM + m] = live ? st.cnt[m] : 0;
+        out.counts_weighted[(size_t)b * kMaxM + m] = live ? st.cw[m] : 0.0;
+    }
+    for (int n = T.tid; n < N; n += T.nthreads) out.vp_assoc[base + n] = have_vps ? im.assoc[n] : -1;
+    if (out.decision_metric && have_vps) {
+        double* dm = out.decision_metric + (size_t)kMaxM * base;
+        for (size_t e = T.tid; e < (size_t)st.M * N; e += T.nthreads) dm[e] = im.w[e];
+    }
+    team_sync();
+    if (T.tid == 0) { st.phase = PH_DONE; st.run_e = 0; st.run_w = 0; st.done = 1; st.status = status; st.iters_out = iters; }
+    team_sync();
+}
+
+// ask for an E-step (and weight matrix) on cur (vsel 0) or nxt (vsel 1); POST resumes in `phase`
+VPK_DEVFN void request(EmSlot& st, int vsel, int phase, const Team& T) {
+    team_sync();
+    if (T.tid == 0) { st.vsel = vsel; st.phase = phase; st.run_e = 1; st.run_w = 1; }
+    prepare_estep(st, vsel ? st.nxt : st.cur, T);
+}
+
+// ---------------------------------------------------------------------------
+// INIT: per-line constants are done by the caller; this sets up the hypotheses
+// and asks for the first superstep.  Returns false if the slot finished.
+// ---------------------------------------------------------------------------
+VPK_DEVFN bool init_slot(EmSlot& st, InitScratch& isc, const Img& im, const EmOut& out, const vpk_em_config& cfg,
+                         const uint8_t* sphere, int S, const double* init_vp, int n_init, const Team& T) {
+    if (T.tid == 0) { st.M = 0; st.done = 0; st.iter = 0; st.vidx = 0; st.run_e = 0; st.run_w = 0; st.iters_out = 0; }
+    team_sync();
+    if (im.N == 0) { write_result(out, im, st, VPK_EM_NO_INITIAL_VPS, 0, false, T); return false; }
+    const bool have_init = init_vp != nullptr;
+    init_prior_and_vps(st, isc, sphere, S, cfg.num_init_vp, have_init, T);
+    if (have_init) {
+        if (T.tid == 0) {
+            int M = imin(n_init, kMaxM);
+            for (int m = 0; m < M; ++m) {
+                const double* v = init_vp + 3 * (size_t)m;
+                double nr = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+                st.cur[m][0] = v[0] / nr; st.cur[m][1] = v[1] / nr; st.cur[m][2] = v[2] / nr;
+            }
+            st.M = M;
+        }
+        team_sync();
+    }
+    if (st.M == 0) { write_result(out, im, st, VPK_EM_NO_INITIAL_VPS, 0, false, T); return false; }
+    for (int m = T.tid; m < kMaxM; m += T.nthreads) {
+        st.s[m] = st.sigma_prior * 1e-6;                  // s_init (:219)
+        st.nxt[m][0] = st.nxt[m][1] = st.nxt[m][2] = 0.0;
+    }
+    request(st, 0, PH_INIT_COUNTS, T);
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// POST: consume the E/W results of the superstep according to st.phase and run
+// the reference's control flow until the next E-step is needed or the image is
+// finished.
+// ---------------------------------------------------------------------------
+VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut& out, const vpk_em_config& cfg,
+                         double* big, size_t big_cap, int* big_lock, const Team& T) {
+    const int N = im.N;
+    const double max_stdd = 1e-6;            // angle mode (:197)
+    int ph = st.phase;
+    while (true) {
+        team_sync();
+        switch (ph) {
+        case PH_INIT_COUNTS: {
+            line_counts(im, st, cfg.outlier_thresh, T);
+            for (int m = T.tid; m < st.M; m += T.nthreads) sc.rem[m] = st.cnt[m] < 3;
+            compact_vps(st, sc.rem, T);
+            if (T.tid == 0) st.iter = 0;
+            ph = CT_ITER_BEGIN;
+            break;
+        }
+        case CT_ITER_BEGIN: {
+            const int i = st.iter;
+            if (i >= cfg.num_iter || st.M == 0) {             // "No VPs left!" (:258) / loop exhausted (:450)
+                write_result(out, im, st, VPK_EM_NO_VPS_LEFT, 0, false, T);
+                return;
+            }
+            if (i % cfg.split_merge_freq == 0 && i > 0 && i < 100 && cfg.do_split) {     // :262
+                request(st, 0, PH_SPLIT, T);
+                return;
+            }
+            request(st, 0, PH_MSTEP, T);                       // :273, :282
+            return;
+        }
+        case PH_SPLIT: {
+            int changed = split_best_vp(im, st, sc, cfg.merge_thresh, big, big_cap, big_lock, T);
+            // no candidate: the E/W results of this superstep are exactly what :273/:282 recompute
+            if (changed < 0) { ph = PH_MSTEP; break; }
+            // otherwise the split scratch has overwritten lvsq/pvl/w
+            request(st, 0, PH_MSTEP, T);
+            return;
+        }
+        case PH_MSTEP: {
+            // ---- M-step (:284-322), one warp per VP
+            const int M = st.M;
+            for (int m = T.warp; m < M; m += T.nwarps) {
+                if (!cfg.do_iterations) {
+                    if (T.lane == 0) { sc.rem[m] = 0; sc.err[m] = 0.0; for (int c = 0; c < 3; ++c) st.nxt[m][c] = st.cur[m][c]; }
+                    continue;
+                }
+                double nv[3];
+                bool okv = refit_vp(im, im.w + (size_t)m * N, nullptr, -1, nv, T);
+                double sv = okv ? variance_update(im, m, -1, T) : 0.0;
+                if (T.lane == 0) {
+                    int rem = 0;
+                    double err = 0.0;
+                    if (!okv) rem = 1;
+                    else {
+                        st.nxt[m][0] = nv[0]; st.nxt[m][1] = nv[1]; st.nxt[m][2] = nv[2];
+                        sv = isnan(sv) ? sv : fmin(sv, max_stdd);                  // :306
+                        sv = isnan(sv) ? sv : fmax(sv, cfg.s_thresh);              // :307
+                        st.s[m] = sv;
+                        if (isnan(sv)) rem = 1;
+                        else {
+                            double d = fabs(st.cur[m][0] * nv[0] + st.cur[m][1] * nv[1] + st.cur[m][2] * nv[2]);
+                            err = acos(fmin(d, 1.0));                               // :312
+                            if (isnan(d)) err = d;
+                            if (err > 1.5) rem = 1;
+                        }
+                    }
+                    sc.rem[m] = rem;
+                    sc.err[m] = err;
+                }
+            }
+            team_sync();
+            if (T.tid == 0) {
+                double mx = 0.0;
+                for (int m = 0; m < M; ++m) {
+                    double e = sc.err[m];
+                    if (isnan(e) || isnan(mx)) mx = nan("");      // numpy.maximum propagates NaN
+                    else if (e > mx) mx = e;
+                }
+                sc.da = mx;
+            }
+            team_sync();
+            const double max_err = sc.da;
+            compact_vps(st, sc.rem, T);
+            // the E-step of :332 only clamps s in place (calc_plv :139); its probabilities are
+            // recomputed before every use (:273, :344, merge_vps :650)
+            for (int m = T.tid; m < st.M; m += T.nthreads) {
+                double sm = st.s[m] > 1e-200 ? st.s[m] : 1e-200;
+                if (isnan(st.s[m])) sm = 1e-200;
+                st.s[m] = sm;
+            }
+            team_sync();
+            const int i = st.iter;
+            if (max_err < cfg.final_convergence || i == cfg.num_iter - 1 || !cfg.do_iterations) {   // :335
+                if (cfg.do_merge) {                                                  // :339
+                    if (T.tid == 0) { st.merge_thresh = cfg.merge_thresh * 10; st.after_merge = CT_FINAL_A; }
+                    ph = CT_MERGE_LOOP;
+                } else ph = CT_FINAL_A;
+                break;
+            }
+            if (i % cfg.split_merge_freq == 0 && i > 0 && i <= 100 + cfg.split_merge_freq && cfg.do_merge) {   // :444
+                if (T.tid == 0) { st.merge_thresh = cfg.merge_thresh; st.after_merge = CT_ADVANCE; }
+                ph = CT_MERGE_LOOP;
+                break;
+            }
+            ph = CT_ADVANCE;
+            break;
+        }
+        case CT_MERGE_LOOP: {
+            // E10: merge_vps (vp_localisation.py:633-684) on the nxt row set
+            const int M = st.M;
+            if (M <= 1) { ph = st.after_merge; break; }
+            // closest pair: first minimum in row-major order of the (M,M) angle matrix (diag = pi)
+            if (T.tid == 0) {
+                double best = INFINITY;
+                int bj = 0, bk = 0;
+                bool nanfound = false;
+                for (int j = 0; j < M && !nanfound; ++j)
+                    for (int k = 0; k < M; ++k) {
+                        double a;
+                        if (j == k) a = kPi;
+                        else {
+                            double c = st.nxt[k][0] * st.nxt[j][0] + st.nxt[k][1] * st.nxt[j][1] + st.nxt[k][2] * st.nxt[j][2];
+                            c = fmin(fmax(c, -1.0), 1.0);
+                            a = fabs(acos(fmin(fmax(fabs(c), -1.0), 1.0)));
+                            if (isnan(c)) a = c;
+                        }
+                        if (isnan(a)) { best = a; bj = j; bk = k; nanfound = true; break; }   // numpy.argmin returns the first NaN
+                        if (a < best) { best = a; bj = j; bk = k; }
+                    }
+                sc.ia = bj; sc.ib = bk; sc.da = best;
+            }
+            team_sync();
+            if (!(sc.da < st.merge_thresh)) { ph = st.after_merge; break; }
+            if (T.tid == 0) { st.merge_j = sc.ia; st.merge_k = sc.ib; }
+            request(st, 1, PH_MERGE_EVAL, T);
+            return;
+        }
+        case PH_MERGE_EVAL: {
+            const int j = st.merge_j, k = st.merge_k, M = st.M;
+            if (T.warp == 0) {
+                double nv[3];
+                bool okv = refit_vp(im, im.w + (size_t)j * N, im.w + (size_t)k * N, -1, nv, T);
+                double sk = variance_update(im, k, j, T);
+                if (T.lane == 0) {
+                    st.s[k] = sk;                                  // assigned before the test (:666)
+                    sc.flag = (okv && !(sk > 0.01)) ? 1 : 0;       // max_stdd = 0.01 (:633, :668)
+                    if (sc.flag) { st.nxt[k][0] = nv[0]; st.nxt[k][1] = nv[1]; st.nxt[k][2] = nv[2]; }
+                }
+            }
+            team_sync();
+            if (!sc.flag) { ph = st.after_merge; break; }
+            for (int m = T.tid; m < M; m += T.nthreads) sc.rem[m] = (m == j);
+            compact_vps(st, sc.rem, T);
+            ph = CT_MERGE_LOOP;
+            break;
+        }
+        case CT_ADVANCE: {
+            // v[i+1] becomes the current set
+            for (int m = T.tid; m < st.M; m += T.nthreads)
+                for (int c = 0; c < 3; ++c) { st.cur[m][c] = st.nxt[m][c]; st.nxt[m][c] = 0.0; }
+            team_sync();
+            if (T.tid == 0) st.iter += 1;
+            ph = CT_ITER_BEGIN;
+            break;
+        }
+        case CT_FINAL_A: {
+            request(st, 0, PH_HARD_REFIT, T);                   // :344 (index i, sic)
+            return;
+        }
+        case PH_HARD_REFIT: {
+            argmax_assoc(im, st.M, T);
+            // hard-assignment refit (:353-392)
+            const int M2 = st.M;
+            for (int m = T.warp; m < M2; m += T.nwarps) {
+                bool have = false;
+                for (int n = T.lane; n < N; n += T.lanes) have = have || (im.assoc[n] == m);
+                have = warp_any(have);
+                if (!have) { if (T.lane == 0) sc.rem[m] = 0; continue; }
+                double nv[3];
+                bool okv = refit_vp(im, im.w + (size_t)m * N, nullptr, m, nv, T);
+                double sv = okv ? variance_update(im, m, -1, T) : 0.0;
+                if (T.lane == 0) {
+                    int rem = 0;
+                    if (!okv) rem = 1;
+                    else {
+                        st.nxt[m][0] = nv[0]; st.nxt[m][1] = nv[1]; st.nxt[m][2] = nv[2];
+                        sv = isnan(sv) ? sv : fmin(sv, max_stdd);               // :377
+                        st.s[m] = sv;
+                        if (isnan(sv) || sv < cfg.s_thresh) rem = 1;            // :379
+                        else {
+                            double d = fabs(st.cur[m][0] * nv[0] + st.cur[m][1] * nv[1] + st.cur[m][2] * nv[2]);
+                            double err = acos(fmin(d, 1.0));
+                            if (err > 1.5) rem = 1;
+                        }
+                    }
+                    sc.rem[m] = rem;
+                }
+            }
+            compact_vps(st, sc.rem, T);
+            if (st.M == 0) {                                    // "decision metric is empty" (:400-404)
+                write_result(out, im, st, VPK_EM_NO_VPS_LEFT, 0, false, T);
+                return;
+            }
+            request(st, 0, PH_KEEP_WINNERS, T);                 // :398
+            return;
+        }
+        case PH_KEEP_WINNERS: {
+            // keep only the VPs that win at least one line (:406-413)
+            argmax_assoc(im, st.M, T);
+            for (int m = T.tid; m < st.M; m += T.nthreads) sc.rem[m] = 1;
+            team_sync();
+            for (int n = T.tid; n < N; n += T.nthreads) sc.rem[im.assoc[n]] = 0;
+            compact_vps(st, sc.rem, T);
+            if (T.tid == 0) st.vidx = 0;
+            request(st, 1, PH_FINAL_COUNTS, T);                 // :415 (index i+1)
+            return;
+        }
+        case PH_FINAL_COUNTS: {
+            line_counts(im, st, cfg.outlier_thresh, T);
+            // drop VPs with too few lines, front to back (:423-437)
+            if (T.tid == 0) {
+                int v = st.vidx;
+                while (v < st.M && !(st.cnt[v] < cfg.num_min_lines)) ++v;
+                st.vidx = v;
+            }
+            team_sync();
+            const int v = st.vidx;
+            if (v >= st.M) {
+                const bool ok = st.M > 0;
+                write_result(out, im, st, ok ? VPK_EM_OK : VPK_EM_NO_VPS_LEFT, st.iter, ok, T);
+                return;
+            }
+            for (int m = T.tid; m < st.M; m += T.nthreads) sc.rem[m] = (m == v);
+            compact_vps(st, sc.rem, T);
+            if (st.M == 0) {                                    // the reference crashes here (argmax of an empty axis)
+                write_result(out, im, st, VPK_EM_NO_VPS_LEFT, st.iter, false, T);
+                return;
+            }
+            request(st, 1, PH_FINAL_COUNTS, T);
+            return;
+        }
+        default:
+            return;
+        }
+    }
+}
+
+}  // namespace em
+}  // namespace vpk
