@@ -36,7 +36,7 @@ using namespace em;
 
 static constexpr int kInitThreads = 256;
 static constexpr int kPairThreads = 256;
-static constexpr int kEThreads = 128;
+static constexpr int kEThreads = 256;
 static constexpr int kWThreads = 256;
 static constexpr int kJR = 32;             // lsim rows per pipeline stage of the W kernel
 static constexpr int kStages = 4;
@@ -192,24 +192,72 @@ __global__ void __launch_bounds__(kInitThreads) em_init_kernel(EmParams P) {
 }
 
 // ---------------------------------------------------------------------------
-// em_estep: E5 for 128 lines of one active slot
+// em_estep: E5 for 32 lines of one active slot.  lane = line, warp w = VP rows
+// w, w+8, ...; the per-line normaliser p(l) is the sum of the 8 warp partials in
+// warp order; the W operand tile is staged in shared memory and written with
+// contiguous stores.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEThreads) em_estep_kernel(EmParams P, int cur) {
+    constexpr int NW = kEThreads / 32, kMI = kMaxM / NW;
     __shared__ double c_pv[kMaxM], c_vx[kMaxM], c_vy[kMaxM], c_two_s[kMaxM], c_coef[kMaxM];
+    __shared__ double s_pl[NW][32];
+    __shared__ double s_wt[kMaxM / kMP][32][kMP + 1];       // +1: conflict-free column writes
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) P.ctl[cur ^ 1] = 0;     // next superstep's list starts empty
     if ((int)blockIdx.y >= P.ctl[cur]) return;
     const int slot = P.lists[cur * P.n_slots + blockIdx.y];
     const EmSlot& st = P.slots[slot];
     if (!st.run_e) return;
-    const int N = st.N, M = st.M;
-    if ((int)(blockIdx.x * kEThreads) >= N) return;
-    for (int m = threadIdx.x; m < M; m += kEThreads) {
+    const int N = st.N, M = st.M, n0 = blockIdx.x * 32;
+    if (n0 >= N) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int m = tid; m < M; m += kEThreads) {
         c_pv[m] = st.pv[m]; c_vx[m] = st.vx[m]; c_vy[m] = st.vy[m]; c_two_s[m] = st.two_s[m]; c_coef[m] = st.coef[m];
     }
     __syncthreads();
     const Img im = make_img(N, P.ws + st.ws_off, P.segs + 4 * (size_t)st.base);
-    const int n = blockIdx.x * kEThreads + threadIdx.x;
-    if (n < N) estep_line(im, M, c_pv, c_vx, c_vy, c_two_s, c_coef, n);
+    const int n = n0 + lane;
+    const bool live = n < N;
+    const LineGeom g = line_geom(im.lp, live ? n : 0);
+    double plv[kMI];
+    double part = 0.0;
+#pragma unroll
+    for (int mi = 0; mi < kMI; ++mi) {
+        const int m = warp + NW * mi;
+        plv[mi] = 0.0;
+        if (m < M) {
+            double lvsq;
+            estep_nm(g, c_vx[m], c_vy[m], c_two_s[m], c_coef[m], lvsq, plv[mi]);
+            if (live) im.lvsq[(size_t)m * N + n] = lvsq;
+            part += plv[mi] * c_pv[m];
+        }
+    }
+    s_pl[warp][lane] = part;
+    __syncthreads();
+    double pl = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) pl += s_pl[w][lane];
+    if (pl < 1e-12) pl = 1e-12;                                         // :117 (NaN stays NaN)
+    const double lw = live ? im.lweight[n] : 0.0;
+    const int passes = (M + kMP - 1) / kMP;
+#pragma unroll
+    for (int mi = 0; mi < kMI; ++mi) {
+        const int m = warp + NW * mi;
+        if (m < passes * kMP) {
+            double x = 0.0;
+            if (m < M) {
+                x = plv[mi] * c_pv[m] / pl;                             // calc_pvl (:128)
+                if (live) im.pvl[(size_t)m * N + n] = x;
+                x *= lw;                                                // weight_matrix :517
+            }
+            s_wt[m / kMP][lane][m % kMP] = x;
+        }
+    }
+    __syncthreads();
+    const int nl = min(32, N - n0);
+    for (int p = 0; p < passes; ++p) {
+        double* dst = im.wt + ((size_t)p * N + n0) * kMP;
+        for (int e = tid; e < nl * kMP; e += kEThreads) dst[e] = s_wt[p][e / kMP][e % kMP];
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -386,7 +434,7 @@ static int em_wave(vpk_ctx* ctx, EmState* st, EmParams& P, int n, int nmax) {
             const int cur = step & 1;
             {
                 KernelScope ks(ctx, "em_estep");
-                em_estep_kernel<<<dim3((nmax + kEThreads - 1) / kEThreads, bound), kEThreads, 0, sm>>>(P, cur);
+                em_estep_kernel<<<dim3((nmax + 31) / 32, bound), kEThreads, 0, sm>>>(P, cur);
                 VPK_TRY(check_launch("em_estep"));
             }
             {

@@ -342,6 +342,45 @@ struct PostScratch {
     double da;
 };
 
+// Block-wide arg-min of (v, i) pairs: smallest v, ties -> smallest i; i < 0 = no candidate.
+// Result in sc.da / sc.ia (ia < 0: no candidate at all).  Deterministic.
+#if defined(__CUDACC__)
+VPK_DEVFN void team_min_pair(double v, int i, PostScratch& sc, const Team& T) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (oi >= 0 && (i < 0 || ov < v || (ov == v && oi < i))) { v = ov; i = oi; }
+    }
+    if (T.lane == 0) { sc.redv[T.warp] = v; sc.redi[T.warp] = i; }
+    __syncthreads();
+    if (T.warp == 0) {
+        v = T.lane < T.nwarps ? sc.redv[T.lane] : 0.0;
+        i = T.lane < T.nwarps ? sc.redi[T.lane] : -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, v, o);
+            int oi = __shfl_xor_sync(0xffffffffu, i, o);
+            if (oi >= 0 && (i < 0 || ov < v || (ov == v && oi < i))) { v = ov; i = oi; }
+        }
+        if (T.lane == 0) { sc.da = v; sc.ia = i; }
+    }
+    __syncthreads();
+}
+// warp-wide version, result in every lane
+VPK_DEV void warp_min_pair(double& v, int& i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (oi >= 0 && (i < 0 || ov < v || (ov == v && oi < i))) { v = ov; i = oi; }
+    }
+}
+#else
+inline void team_min_pair(double v, int i, PostScratch& sc, const Team&) { sc.da = v; sc.ia = i; }
+inline void warp_min_pair(double&, int&) {}
+#endif
+
 struct InitScratch {
     double resp[kCells];
     double cand[kCells][3];
@@ -516,22 +555,33 @@ VPK_DEVFN void prepare_estep(EmSlot& st, const double (*v)[3], const Team& T) {
     team_sync();
 }
 
-// E5 part 2 for line n (probability_functions.py:99-147): lvsq, p(v|l), and the
-// W-kernel operand wt = p(v|l) * lweight.  c: pv/vx/vy/two_s/coef of the slot.
+// E5 part 2 (probability_functions.py:99-147).  Per-line constants of calc_lvsq_angle (:157-176):
+struct LineGeom { double mx, my, bx, by, nb; };
+VPK_DEV LineGeom line_geom(const double* lp, int n) {
+    Seg sg = load_seg(lp, n);
+    LineGeom g;
+    g.mx = 0.5 * (sg.x1 + sg.x2); g.my = 0.5 * (sg.y1 + sg.y2);
+    g.bx = sg.x1 - sg.x2; g.by = sg.y1 - sg.y2;
+    g.nb = sqrt(g.bx * g.bx + g.by * g.by);
+    return g;
+}
+// one (line, VP) pair: lvsq (:174) and p(l|v) (calc_plv :140-145)
+VPK_DEV void estep_nm(const LineGeom& g, double vx, double vy, double two_s, double coef, double& lvsq, double& plv) {
+    double ax = g.mx - vx, ay = g.my - vy;
+    double c = (ax * g.bx + ay * g.by) / (sqrt(ax * ax + ay * ay) * g.nb);
+    double q = 1.0 - fabs(c);
+    lvsq = q * q;
+    plv = exp(-(lvsq / two_s)) * coef;
+}
+// whole line (host build): lvsq, p(v|l), and the W-kernel operand wt = p(v|l) * lweight
 VPK_DEV void estep_line(const Img& im, int M, const double* pv, const double* vx, const double* vy, const double* two_s,
                         const double* coef, int n) {
     const int N = im.N;
-    Seg sg = load_seg(im.lp, n);
-    double mx = 0.5 * (sg.x1 + sg.x2), my = 0.5 * (sg.y1 + sg.y2);
-    double bx = sg.x1 - sg.x2, by = sg.y1 - sg.y2;
-    double nb = sqrt(bx * bx + by * by);
+    const LineGeom g = line_geom(im.lp, n);
     double pl = 0.0;
     for (int m = 0; m < M; ++m) {
-        double ax = mx - vx[m], ay = my - vy[m];
-        double c = (ax * bx + ay * by) / (sqrt(ax * ax + ay * ay) * nb);
-        double q = 1.0 - fabs(c);
-        double lvsq = q * q;                                            // calc_lvsq_angle (:174)
-        double plv = exp(-(lvsq / two_s[m])) * coef[m];                 // calc_plv (:140-145)
+        double lvsq, plv;
+        estep_nm(g, vx[m], vy[m], two_s[m], coef[m], lvsq, plv);
         im.lvsq[(size_t)m * N + n] = lvsq;
         im.pvl[(size_t)m * N + n] = plv;
         pl += plv * pv[m];
@@ -692,49 +742,60 @@ VPK_DEVFN void compact_vps(EmSlot& st, const int* rem, const Team& T) {
 // AgglomerativeClustering(linkage='average', n_clusters=2) computes on a
 // complete connectivity graph); labels follow _hc_cut: label 0 = the root's
 // child with the larger node id.
-VPK_DEVFN void average_linkage_two(double* D, int n, int* rep, int* nodeid, double* csize, PostScratch& sc, const Team& T) {
+VPK_DEVFN void average_linkage_two(double* D, int n, int* rep, int* nodeid, double* csize, double* rmin, int* rarg,
+                                    int* need, PostScratch& sc, const Team& T) {
+    // rmin[a] / rarg[a]: the first minimum of row a over the active columns b > a.  The global
+    // minimum over active pairs a < b with lexicographic tie-break is then the smallest rmin, ties
+    // to the smallest a.  After a merge only the rows whose cached minimum involved the merged
+    // pair are rescanned.
     const int tid = T.tid, NT = T.nthreads;
-    for (int i = tid; i < n; i += NT) { rep[i] = i; nodeid[i] = i; csize[i] = 1.0; }
+    for (int i = tid; i < n; i += NT) { rep[i] = i; nodeid[i] = i; csize[i] = 1.0; need[i] = 1; }
     team_sync();
-    for (int step = 0; step < n - 2; ++step) {
-        // global minimum over active pairs a < b, lexicographic tie-break
-        double bd = INFINITY;
-        int ba = -1, bb = -1;
-        for (int a = tid; a < n; a += NT) {
-            if (nodeid[a] < 0) continue;
+    for (int step = 0; step < n - 1; ++step) {
+        // (re)scan the flagged rows, one warp per row
+        for (int a = T.warp; a < n; a += T.nwarps) {
+            if (nodeid[a] < 0 || !need[a]) continue;
+            double bd = INFINITY;
+            int bb = -1;
             const double* row = D + (size_t)a * n;
-            for (int b = a + 1; b < n; ++b) {
+            for (int b = a + 1 + T.lane; b < n; b += T.lanes) {
                 if (nodeid[b] < 0) continue;
                 double d = row[b];
-                if (d < bd) { bd = d; ba = a; bb = b; }
+                if (bb < 0 || d < bd) { bd = d; bb = b; }
             }
+            warp_min_pair(bd, bb);
+            if (T.lane == 0) { rmin[a] = bd; rarg[a] = bb; need[a] = 0; }
         }
-        sc.redv[tid] = bd; sc.redi[tid] = ba; sc.redj[tid] = bb;
         team_sync();
-        for (int o = NT / 2; o > 0; o >>= 1) {
-            if (tid < o) {
-                double od = sc.redv[tid + o];
-                int oa = sc.redi[tid + o], ob = sc.redj[tid + o];
-                bool take = oa >= 0 && (sc.redi[tid] < 0 || od < sc.redv[tid] ||
-                                        (od == sc.redv[tid] && (oa < sc.redi[tid] || (oa == sc.redi[tid] && ob < sc.redj[tid]))));
-                if (take) { sc.redv[tid] = od; sc.redi[tid] = oa; sc.redj[tid] = ob; }
-            }
-            team_sync();
+        if (step == n - 2) break;
+        double bd = INFINITY;
+        int ba = -1;
+        for (int a = tid; a < n; a += NT) {
+            if (nodeid[a] < 0 || rarg[a] < 0) continue;
+            double d = rmin[a];
+            if (ba < 0 || d < bd) { bd = d; ba = a; }
         }
-        const int a = sc.redi[0], b = sc.redj[0];
-        team_sync();
+        team_min_pair(bd, ba, sc, T);
+        const int a = sc.ia;
         if (a < 0) break;
+        const int b = rarg[a];
         const double na = csize[a], nb = csize[b];
+        team_sync();
         for (int c = tid; c < n; c += NT) {
             if (c == a || c == b || nodeid[c] < 0) continue;
             double dn = (na * D[(size_t)a * n + c] + nb * D[(size_t)b * n + c]) / (na + nb);   // average_merge
             D[(size_t)a * n + c] = dn;
             D[(size_t)c * n + a] = dn;
+            if (c < a) {
+                if (rarg[c] == a || rarg[c] == b) need[c] = 1;
+                else if (dn < rmin[c] || (dn == rmin[c] && a < rarg[c])) { rmin[c] = dn; rarg[c] = a; }
+            } else if (c < b) {
+                if (rarg[c] == b) need[c] = 1;
+            }
         }
         for (int i = tid; i < n; i += NT)
             if (rep[i] == b) rep[i] = a;
-        team_sync();
-        if (tid == 0) { csize[a] = na + nb; nodeid[a] = n + step; nodeid[b] = -1; }
+        if (tid == 0) { csize[a] = na + nb; nodeid[a] = n + step; nodeid[b] = -1; need[a] = 1; }
         team_sync();
     }
     // the two survivors; label 0 = larger node id
@@ -821,8 +882,8 @@ VPK_DEVFN int split_best_vp(const Img& im, EmSlot& st, PostScratch& sc, double m
     const int worst = sc.ia;
     if (worst < 0) return -1;
     const int nw = st.cnt[worst];
-    // scratch layout (doubles): D[nw*nw] | csize[nw] | ints: idx[nw] rep[nw] nodeid[nw]
-    size_t need = (size_t)nw * nw + nw + (3 * (size_t)nw + 1) / 2 + 4;
+    // scratch layout (doubles): D[nw*nw] | csize[nw] | rmin[nw] | ints: idx rep nodeid rarg flag [nw each]
+    size_t need = (size_t)nw * nw + 2 * (size_t)nw + (5 * (size_t)nw + 1) / 2 + 4;
     double* scratch = im.lvsq;
     bool locked = false;
     // the line -> VP association and the line weights live outside the scratch region; the E/W
@@ -839,9 +900,12 @@ VPK_DEVFN int split_best_vp(const Img& im, EmSlot& st, PostScratch& sc, double m
     }
     double* D = scratch;
     double* csize = D + (size_t)nw * nw;
-    int* idx = reinterpret_cast<int*>(csize + nw);
+    double* rmin = csize + nw;
+    int* idx = reinterpret_cast<int*>(rmin + nw);
     int* rep = idx + nw;
     int* nodeid = rep + nw;
+    int* rarg = nodeid + nw;
+    int* rflag = rarg + nw;
     if (tid == 0) {
         int k = 0;
         for (int n = 0; n < N; ++n) if (im.assoc[n] == worst) idx[k++] = n;
@@ -854,7 +918,7 @@ VPK_DEVFN int split_best_vp(const Img& im, EmSlot& st, PostScratch& sc, double m
         D[e] = d;
     }
     team_sync();
-    average_linkage_two(D, nw, rep, nodeid, csize, sc, T);
+    average_linkage_two(D, nw, rep, nodeid, csize, rmin, rarg, rflag, sc, T);
     // per cluster: smallest right-singular vector of the lweight-scaled lines (:580-602)
     for (int c = T.warp; c < 2; c += T.nwarps) {
         double g[6] = {0, 0, 0, 0, 0, 0};
@@ -1085,27 +1149,32 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
             // E10: merge_vps (vp_localisation.py:633-684) on the nxt row set
             const int M = st.M;
             if (M <= 1) { ph = st.after_merge; break; }
-            // closest pair: first minimum in row-major order of the (M,M) angle matrix (diag = pi)
-            if (T.tid == 0) {
-                double best = INFINITY;
-                int bj = 0, bk = 0;
-                bool nanfound = false;
-                for (int j = 0; j < M && !nanfound; ++j)
-                    for (int k = 0; k < M; ++k) {
-                        double a;
-                        if (j == k) a = kPi;
-                        else {
-                            double c = st.nxt[k][0] * st.nxt[j][0] + st.nxt[k][1] * st.nxt[j][1] + st.nxt[k][2] * st.nxt[j][2];
-                            c = fmin(fmax(c, -1.0), 1.0);
-                            a = fabs(acos(fmin(fmax(fabs(c), -1.0), 1.0)));
-                            if (isnan(c)) a = c;
-                        }
-                        if (isnan(a)) { best = a; bj = j; bk = k; nanfound = true; break; }   // numpy.argmin returns the first NaN
-                        if (a < best) { best = a; bj = j; bk = k; }
+            // closest pair: first minimum in row-major order of the (M,M) angle matrix (diag = pi);
+            // numpy.argmin returns the first NaN if there is one (key -inf)
+            {
+                double bv = INFINITY;
+                int be = -1;
+                for (int e = T.tid; e < M * M; e += T.nthreads) {
+                    const int j = e / M, k = e % M;
+                    double a;
+                    if (j == k) a = kPi;
+                    else {
+                        double c = st.nxt[k][0] * st.nxt[j][0] + st.nxt[k][1] * st.nxt[j][1] + st.nxt[k][2] * st.nxt[j][2];
+                        c = fmin(fmax(c, -1.0), 1.0);
+                        a = fabs(acos(fmin(fmax(fabs(c), -1.0), 1.0)));
+                        if (isnan(c)) a = c;
                     }
-                sc.ia = bj; sc.ib = bk; sc.da = best;
+                    if (isnan(a)) a = -INFINITY;
+                    if (be < 0 || a < bv) { bv = a; be = e; }
+                }
+                team_min_pair(bv, be, sc, T);
+                if (T.tid == 0) {
+                    const int e = sc.ia;
+                    sc.ib = e % M; sc.ia = e / M;
+                    if (sc.da == -INFINITY) sc.da = nan("");
+                }
+                team_sync();
             }
-            team_sync();
             if (!(sc.da < st.merge_thresh)) { ph = st.after_merge; break; }
             if (T.tid == 0) { st.merge_j = sc.ia; st.merge_k = sc.ib; }
             request(st, 1, PH_MERGE_EVAL, T);
