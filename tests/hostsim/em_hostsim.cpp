@@ -24,17 +24,17 @@ extern "C" int hostsim_em(const double* lines, const double* segs, int N, const 
     if (cfg->use_weights) {
         // em_pair_kernel, sequentially
         for (int k = 0; k < N; ++k) {
-            const Seg sk = load_seg(im.lp, k);
+            const SegPre sk = seg_pre(load_seg(im.lp, k));
             double cd[kK1]; int cj[kK1]; int cnt = 0;
             double cs = 0.0;
             for (int j = 0; j < N; ++j) {
                 double val = 0.0;
-                if (j == k) knn_insert(cd, cj, 1, cnt, 4.0, j);
+                if (j == k) knn_insert(cd, cj, 1, cnt, 16.0, j);
                 else {
-                    const Seg sj = load_seg(im.lp, j);
-                    const double dist = seg_distance(sj, sk);
-                    val = similarity(sj, sk, dist);
-                    knn_insert(cd, cj, 1, cnt, dist, j);
+                    const SegPre sj = seg_pre(load_seg(im.lp, j));
+                    const double d2 = seg_distance2(sj, sk);
+                    val = similarity_pre(sj, sk, d2);
+                    knn_insert(cd, cj, 1, cnt, d2, j);
                 }
                 im.lsim[lsim_index(N, j, k)] = val;
                 cs += val;
@@ -55,14 +55,14 @@ extern "C" int hostsim_em(const double* lines, const double* segs, int N, const 
     while (active && steps < 100000) {
         ++steps;
         if (st->run_e)
-            for (int n = 0; n < N; ++n) estep_line(im, st->M, st->pv, st->vx, st->vy, st->two_s, st->coef, n);
+            for (int n = 0; n < N; ++n) estep_line(im, st->M, st->pv, st->vx, st->vy, st->inv2s, st->coef, n);
         if (st->run_w)
             for (int m = 0; m < st->M; ++m)
                 for (int k = 0; k < N; ++k) {
                     double acc = 0.0;
                     if (cfg->use_weights)
-                        for (int j = 0; j < N; ++j) acc += im.wt[wt_index(N, j, m)] * im.lsim[lsim_index(N, j, k)];
-                    im.w[(size_t)m * N + k] = wmat_finish(im.wt[wt_index(N, k, m)], im.lweight[k], im.colsum[k], acc, cfg->wbias);
+                        for (int j = 0; j < N; ++j) acc += im.wt[wt_index(N, j, m, st->M)] * im.lsim[lsim_index(N, j, k)];
+                    im.w[(size_t)m * N + k] = wmat_finish(im.wt[wt_index(N, k, m, st->M)], im.lweight[k], im.colsum[k], acc, cfg->wbias);
                 }
         post_slot(*st, *sc, im, out, *cfg, big.data(), big.size(), &lock, T);
         active = !st->done;

@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(kPairThreads) em_pair_kernel(EmParams P) {
     __shared__ int s_kj[kK1 * kPairThreads];
     __shared__ int s_cnt[kPairThreads];
     __shared__ double s_part[kPairThreads];
+    constexpr int JB = 128;
+    __shared__ SegPre s_seg[JB];                     // per-segment constants of the current block of rows
     const SlotDesc d = P.desc[blockIdx.y];
     const int N = d.N, t = blockIdx.x;
     if (t * kTK >= N) return;
@@ -124,23 +126,30 @@ __global__ void __launch_bounds__(kPairThreads) em_pair_kernel(EmParams P) {
     constexpr int G = kPairThreads / kTK;
     const int k = t * kTK + col;
     const bool live = k < N;
-    const Seg sk = load_seg(im.lp, live ? k : 0);
+    const SegPre sk = seg_pre(load_seg(im.lp, live ? k : 0));
     double* slab = im.lsim + (size_t)t * N * kTK;
     double part = 0.0;
     int cnt = 0;
-    for (int j = g; j < N; j += G) {
-        double val = 0.0;
-        if (live) {
-            if (j == k) knn_insert(s_kd + tid, s_kj + tid, kPairThreads, cnt, 4.0, j);      // diagonal: ldist = 4 (:82), lsim = 0 (:105)
-            else {
-                const Seg sj = load_seg(im.lp, j);
-                const double dist = seg_distance(sj, sk);
-                val = similarity(sj, sk, dist);
-                knn_insert(s_kd + tid, s_kj + tid, kPairThreads, cnt, dist, j);
+    for (int jb = 0; jb < N; jb += JB) {
+        __syncthreads();
+        if (tid < JB && jb + tid < N) s_seg[tid] = seg_pre(load_seg(im.lp, jb + tid));
+        __syncthreads();
+        const int jn = min(JB, N - jb);
+        for (int jj = g; jj < jn; jj += G) {
+            const int j = jb + jj;
+            double val = 0.0;
+            if (live) {
+                if (j == k) knn_insert(s_kd + tid, s_kj + tid, kPairThreads, cnt, 16.0, j);   // diagonal: ldist = 4 (:82), lsim = 0 (:105)
+                else {
+                    const SegPre& sj = s_seg[jj];
+                    const double d2 = seg_distance2(sj, sk);
+                    val = similarity_pre(sj, sk, d2);
+                    knn_insert(s_kd + tid, s_kj + tid, kPairThreads, cnt, d2, j);
+                }
             }
+            slab[(size_t)j * kTK + col] = val;
+            part += val;
         }
-        slab[(size_t)j * kTK + col] = val;
-        part += val;
     }
     s_cnt[tid] = cnt;
     s_part[tid] = part;
@@ -199,7 +208,7 @@ __global__ void __launch_bounds__(kInitThreads) em_init_kernel(EmParams P) {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEThreads) em_estep_kernel(EmParams P, int cur) {
     constexpr int NW = kEThreads / 32, kMI = kMaxM / NW;
-    __shared__ double c_pv[kMaxM], c_vx[kMaxM], c_vy[kMaxM], c_two_s[kMaxM], c_coef[kMaxM];
+    __shared__ double c_pv[kMaxM], c_vx[kMaxM], c_vy[kMaxM], c_inv2s[kMaxM], c_coef[kMaxM];
     __shared__ double s_pl[NW][32];
     __shared__ double s_wt[kMaxM / kMP][32][kMP + 1];       // +1: conflict-free column writes
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) P.ctl[cur ^ 1] = 0;     // next superstep's list starts empty
@@ -211,7 +220,7 @@ __global__ void __launch_bounds__(kEThreads) em_estep_kernel(EmParams P, int cur
     if (n0 >= N) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int m = tid; m < M; m += kEThreads) {
-        c_pv[m] = st.pv[m]; c_vx[m] = st.vx[m]; c_vy[m] = st.vy[m]; c_two_s[m] = st.two_s[m]; c_coef[m] = st.coef[m];
+        c_pv[m] = st.pv[m]; c_vx[m] = st.vx[m]; c_vy[m] = st.vy[m]; c_inv2s[m] = st.inv2s[m]; c_coef[m] = st.coef[m];
     }
     __syncthreads();
     const Img im = make_img(N, P.ws + st.ws_off, P.segs + 4 * (size_t)st.base);
@@ -226,7 +235,7 @@ __global__ void __launch_bounds__(kEThreads) em_estep_kernel(EmParams P, int cur
         plv[mi] = 0.0;
         if (m < M) {
             double lvsq;
-            estep_nm(g, c_vx[m], c_vy[m], c_two_s[m], c_coef[m], lvsq, plv[mi]);
+            estep_nm(g, c_vx[m], c_vy[m], c_inv2s[m], c_coef[m], lvsq, plv[mi]);
             if (live) im.lvsq[(size_t)m * N + n] = lvsq;
             part += plv[mi] * c_pv[m];
         }
@@ -237,129 +246,217 @@ __global__ void __launch_bounds__(kEThreads) em_estep_kernel(EmParams P, int cur
 #pragma unroll
     for (int w = 0; w < NW; ++w) pl += s_pl[w][lane];
     if (pl < 1e-12) pl = 1e-12;                                         // :117 (NaN stays NaN)
+    const double inv_pl = 1.0 / pl;
     const double lw = live ? im.lweight[n] : 0.0;
     const int passes = (M + kMP - 1) / kMP;
 #pragma unroll
     for (int mi = 0; mi < kMI; ++mi) {
-        const int m = warp + NW * mi;
-        if (m < passes * kMP) {
+        const int m = warp + NW * mi, p = m / kMP, mm = m % kMP;
+        if (p < passes && mm < wpass_stride(M, p)) {
             double x = 0.0;
             if (m < M) {
-                x = plv[mi] * c_pv[m] / pl;                             // calc_pvl (:128)
+                x = plv[mi] * c_pv[m] * inv_pl;                         // calc_pvl (:128)
                 if (live) im.pvl[(size_t)m * N + n] = x;
                 x *= lw;                                                // weight_matrix :517
             }
-            s_wt[m / kMP][lane][m % kMP] = x;
+            s_wt[p][lane][mm] = x;
         }
     }
     __syncthreads();
     const int nl = min(32, N - n0);
     for (int p = 0; p < passes; ++p) {
-        double* dst = im.wt + ((size_t)p * N + n0) * kMP;
-        for (int e = tid; e < nl * kMP; e += kEThreads) dst[e] = s_wt[p][e / kMP][e % kMP];
+        const int ws = wpass_stride(M, p);
+        double* dst = im.wt + (size_t)p * N * kMP + (size_t)n0 * ws;
+        for (int e = tid; e < nl * ws; e += kEThreads) dst[e] = s_wt[p][e / ws][e % ws];
     }
 }
 
 // ---------------------------------------------------------------------------
 // em_wmat: E6, w[m,k] = (wt[k,m] + b lw[k] sum_j wt[j,m] lsim[j,k]) / (1 + b lw[k] colsum[k])
-// (vp_localisation.py:515-524).  CTA = (slot, 64-column slab); the slab (N x 64
-// doubles, contiguous) and the matching rows of wt are streamed through a
-// 4-stage ring of shared-memory buffers by cp.async.bulk; warp w accumulates
-// rows 4w..4w+3 of every 32-row chunk, lane l columns 2l, 2l+1, 16 VP rows per
-// pass; the 8 partial sums per output are added in warp order (deterministic).
+// (vp_localisation.py:515-524).
+//
+// A cluster of CS CTAs owns (slot, 64-column slab); CTA rank r of the cluster
+// streams the rows of chunk range r of the slab (N x 64 doubles, contiguous) and
+// the matching rows of wt through a 4-stage ring of shared-memory buffers filled
+// by cp.async.bulk (full/empty mbarriers, no CTA-wide barrier in the loop: warp
+// 0 re-arms a stage as soon as all 8 warps have released it).  Lane l of a warp
+// accumulates columns 2l, 2l+1; a pass covers up to 32 VP rows as G groups of
+// warps x R rows per thread.  Partial sums are combined in a fixed order: the
+// warps of a CTA through shared memory, then the CTAs of the cluster in rank
+// order through distributed shared memory.  CS depends on N only, so an image's
+// result does not depend on what else is in the batch.
 // ---------------------------------------------------------------------------
 struct WSmem {
     double a[kStages][kJR * kTK];          // lsim rows
-    double b[kStages][kJR * kMP];          // wt rows
-    unsigned long long full[kStages];
+    double b[kStages][kJR * kMP];          // wt rows; reused for the per-CTA partial result (kMP x kTK)
+    unsigned long long full[kStages], empty[kStages];
 };
 
-__global__ void __launch_bounds__(kWThreads, 2) em_wmat_kernel(EmParams P, int cur) {
+__host__ __device__ inline int wmat_split(int N) { return N <= 384 ? 1 : (N <= 768 ? 2 : (N <= 1536 ? 4 : 8)); }
+
+__device__ __forceinline__ void em_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void em_bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t em_cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void em_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double em_ld_dsmem(const double* local, uint32_t rank) {
+    uint32_t addr = em_smem_u32(local), remote;
+    double v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(rank));
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote) : "memory");
+    return v;
+}
+
+// main loop of one pass for R VP rows per thread: chunks [c0, c1) of the slab
+template <int R>
+__device__ __forceinline__ void wmat_pass(WSmem& sm, const double* slab, const double* wtp, int ws, int N, int c0, int c1,
+                                          int G, int& ring, uint64_t policy, double* red, double* part) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NWARP = kWThreads / 32;
+    const int wpg = NWARP / G;                       // warps per group
+    const int g = warp / wpg, wg = warp % wpg;
+    const int rpw = kJR / wpg;                       // rows per warp per chunk
+    double acc[R][2];
+#pragma unroll
+    for (int m = 0; m < R; ++m) acc[m][0] = acc[m][1] = 0.0;
+    const int nch = c1 - c0;
+    int next_issue = 0;                              // warp 0 only
+    auto issue = [&](int i) {                        // chunk c0 + i into ring slot (ring + i) % kStages
+        const int j0 = (c0 + i) * kJR, jn = min(kJR, N - j0), s = (ring + i) % kStages;
+        const uint32_t bar = em_smem_u32(&sm.full[s]);
+        em_mbar_expect_tx(bar, (uint32_t)(jn * (kTK + ws) * sizeof(double)));
+        em_bulk_g2s_hint(em_smem_u32(sm.a[s]), slab + (size_t)j0 * kTK, (uint32_t)(jn * kTK * sizeof(double)), bar, policy);
+        em_bulk_g2s(em_smem_u32(sm.b[s]), wtp + (size_t)j0 * ws, (uint32_t)(jn * ws * sizeof(double)), bar);
+    };
+    for (int i = 0; i < nch; ++i) {
+        const int pos = ring + i, s = pos % kStages;
+        if (warp == 0) {
+            // keep the ring full: chunk q may be issued once ring position (ring + q - kStages) was released
+            while (next_issue < nch && next_issue < i + kStages) {
+                const int q = ring + next_issue;
+                if (q >= kStages) {
+                    const uint32_t eb = em_smem_u32(&sm.empty[q % kStages]);
+                    const uint32_t par = (uint32_t)(((q / kStages) - 1) & 1);
+                    if (next_issue == i) em_mbar_wait(eb, par);
+                    else if (!em_mbar_try_wait(eb, par)) break;
+                }
+                if (lane == 0) issue(next_issue);
+                ++next_issue;
+            }
+            __syncwarp();
+        }
+        em_mbar_wait(em_smem_u32(&sm.full[s]), (uint32_t)((pos / kStages) & 1));
+        const int jn = min(kJR, N - (c0 + i) * kJR);
+        for (int rr = 0; rr < rpw; ++rr) {
+            const int r = wg * rpw + rr;
+            if (r < jn) {
+                const double2 a2 = *reinterpret_cast<const double2*>(&sm.a[s][r * kTK + 2 * lane]);
+                const double2* b2 = reinterpret_cast<const double2*>(&sm.b[s][r * ws + g * R]);
+#pragma unroll
+                for (int q = 0; q < R / 2; ++q) {
+                    const double2 bb = b2[q];
+                    acc[2 * q][0] = fma(bb.x, a2.x, acc[2 * q][0]);
+                    acc[2 * q][1] = fma(bb.x, a2.y, acc[2 * q][1]);
+                    acc[2 * q + 1][0] = fma(bb.y, a2.x, acc[2 * q + 1][0]);
+                    acc[2 * q + 1][1] = fma(bb.y, a2.y, acc[2 * q + 1][1]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) em_mbar_arrive(em_smem_u32(&sm.empty[s]));      // this warp is done with stage s
+    }
+    ring += nch;
+    __syncthreads();                                 // every warp has finished reading the ring
+    // cross-warp reduction in the (now idle) a-ring: red[warp][r][col]
+#pragma unroll
+    for (int m = 0; m < R; ++m)
+        *reinterpret_cast<double2*>(&red[(warp * 16 + m) * kTK + 2 * lane]) = make_double2(acc[m][0], acc[m][1]);
+    __syncthreads();
+    for (int e = tid; e < G * R * kTK; e += kWThreads) {
+        const int mm = e / kTK, col = e % kTK, gg = mm / R, r = mm % R;
+        double sum = 0.0;
+        for (int w = 0; w < wpg; ++w) sum += red[((gg * wpg + w) * 16 + r) * kTK + col];
+        part[e] = sum;
+    }
+}
+
+__global__ void __launch_bounds__(kWThreads, 2) em_wmat_kernel(EmParams P, int cur, int csl) {
     extern __shared__ __align__(128) unsigned char w_smem_raw[];
     WSmem& sm = *reinterpret_cast<WSmem*>(w_smem_raw);
     if ((int)blockIdx.y >= P.ctl[cur]) return;
     const int slot = P.lists[cur * P.n_slots + blockIdx.y];
     const EmSlot& st = P.slots[slot];
     if (!st.run_w) return;
-    const int N = st.N, M = st.M, t = blockIdx.x;
-    if (t * kTK >= N) return;
+    const int N = st.N, M = st.M, t = blockIdx.x / csl;
+    if (t * kTK >= N) return;                       // uniform over the cluster
+    const int rank = csl > 1 ? (int)em_cluster_ctarank() : 0;
+    const int cs = min(wmat_split(N), csl);         // CTAs of the cluster that share this slab
     const Img im = make_img(N, P.ws + st.ws_off, P.segs + 4 * (size_t)st.base);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x;
     const bool stream = P.cfg.use_weights != 0;
     const double bias = P.cfg.wbias;
-    if (P.stats && t == 0 && tid == 0) {
+    if (P.stats && blockIdx.x == 0 && tid == 0) {
         // algorithmic work of this slot's product: the N x N similarity matrix once, 2 M N^2 flops
         atomicAdd(P.stats + 0, (unsigned long long)N * N * sizeof(double));
         atomicAdd(P.stats + 1, 2ull * M * N * N);
         atomicAdd(P.stats + 2, 1ull);
     }
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) em_mbar_init(em_smem_u32(&sm.full[s]), 1);
+        for (int s = 0; s < kStages; ++s) {
+            em_mbar_init(em_smem_u32(&sm.full[s]), 1);
+            em_mbar_init(em_smem_u32(&sm.empty[s]), kWThreads / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
     const int nchunks = (N + kJR - 1) / kJR;
     const int passes = (M + kMP - 1) / kMP;
     const double* slab = im.lsim + (size_t)t * N * kTK;
-    int gc = 0;                                 // chunks consumed so far (ring position, carries over passes)
+    double* red = &sm.a[0][0];
+    double* part = &sm.b[0][0];
+    // chunk range of this CTA
+    int c0 = 0, c1 = 0;
+    if (stream && rank < cs) { c0 = (int)((long long)nchunks * rank / cs); c1 = (int)((long long)nchunks * (rank + 1) / cs); }
+    int ring = 0;                                   // ring position, carries over passes
     for (int pass = 0; pass < passes; ++pass) {
+        int G, R;
+        wpass_shape(M, pass, G, R);
+        const int ws = G * R;
         const double* wtp = im.wt + (size_t)pass * N * kMP;
-        auto issue = [&](int c, int ring) {
-            const int j0 = c * kJR, jn = min(kJR, N - j0), s = ring % kStages;
-            const uint32_t bar = em_smem_u32(&sm.full[s]);
-            em_mbar_expect_tx(bar, (uint32_t)(jn * (kTK + kMP) * sizeof(double)));
-            em_bulk_g2s(em_smem_u32(sm.a[s]), slab + (size_t)j0 * kTK, (uint32_t)(jn * kTK * sizeof(double)), bar);
-            em_bulk_g2s(em_smem_u32(sm.b[s]), wtp + (size_t)j0 * kMP, (uint32_t)(jn * kMP * sizeof(double)), bar);
-        };
-        double acc[kMP][2];
-#pragma unroll
-        for (int m = 0; m < kMP; ++m) acc[m][0] = acc[m][1] = 0.0;
-        if (stream) {
-            if (tid == 0)
-                for (int c = 0; c < min(kStages, nchunks); ++c) issue(c, gc + c);
-            for (int c = 0; c < nchunks; ++c, ++gc) {
-                const int s = gc % kStages;
-                em_mbar_wait(em_smem_u32(&sm.full[s]), (uint32_t)((gc / kStages) & 1));
-                const int jn = min(kJR, N - c * kJR);
-#pragma unroll
-                for (int rr = 0; rr < kJR / (kWThreads / 32); ++rr) {
-                    const int r = warp * (kJR / (kWThreads / 32)) + rr;
-                    if (r < jn) {
-                        const double2 a2 = *reinterpret_cast<const double2*>(&sm.a[s][r * kTK + 2 * lane]);
-                        const double2* b2 = reinterpret_cast<const double2*>(&sm.b[s][r * kMP]);
-#pragma unroll
-                        for (int q = 0; q < kMP / 2; ++q) {
-                            const double2 bb = b2[q];
-                            acc[2 * q][0] = fma(bb.x, a2.x, acc[2 * q][0]);
-                            acc[2 * q][1] = fma(bb.x, a2.y, acc[2 * q][1]);
-                            acc[2 * q + 1][0] = fma(bb.y, a2.x, acc[2 * q + 1][0]);
-                            acc[2 * q + 1][1] = fma(bb.y, a2.y, acc[2 * q + 1][1]);
-                        }
-                    }
+        switch (R) {
+        case 4: wmat_pass<4>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, red, part); break;
+        case 8: wmat_pass<8>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, red, part); break;
+        case 12: wmat_pass<12>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, red, part); break;
+        default: wmat_pass<16>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, red, part); break;
+        }
+        if (csl > 1) em_cluster_sync(); else __syncthreads();          // partial results are complete
+        if (rank == 0) {
+            for (int e = tid; e < ws * kTK; e += kWThreads) {
+                const int mm = e / kTK, col = e % kTK, k = t * kTK + col, m = pass * kMP + mm;
+                if (k < N && m < M) {
+                    double sum = part[e];
+                    for (int r = 1; r < cs; ++r) sum += em_ld_dsmem(part + e, (uint32_t)r);
+                    im.w[(size_t)m * N + k] = wmat_finish(im.wt[(size_t)pass * N * kMP + (size_t)k * ws + mm], im.lweight[k], im.colsum[k], sum, bias);
                 }
-                __syncthreads();                // everyone is done with stage s
-                if (tid == 0 && c + kStages < nchunks) issue(c + kStages, gc + kStages);
             }
         }
-        // cross-warp reduction in the (now idle) ring buffers: red[warp][m][col]
-        double* red = &sm.a[0][0];
-#pragma unroll
-        for (int m = 0; m < kMP; ++m)
-            *reinterpret_cast<double2*>(&red[(warp * kMP + m) * kTK + 2 * lane]) = make_double2(acc[m][0], acc[m][1]);
-        __syncthreads();
-        for (int e = tid; e < kMP * kTK; e += kWThreads) {
-            const int m = e / kTK, col = e % kTK, k = t * kTK + col, mm = pass * kMP + m;
-            if (k < N && mm < M) {
-                double sum = 0.0;
-#pragma unroll
-                for (int w = 0; w < kWThreads / 32; ++w) sum += red[(w * kMP + m) * kTK + col];
-                im.w[(size_t)mm * N + k] = wmat_finish(im.wt[wt_index(N, k, mm)], im.lweight[k], im.colsum[k], sum, bias);
-            }
-        }
-        // red was written through the generic proxy; the next pass' bulk copies write the same
-        // bytes through the async proxy
+        // the ring (generic-proxy writes of red / part) is refilled by the async proxy in the next pass;
+        // remote CTAs must not leave (or overwrite part) while rank 0 still reads their shared memory
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
+        if (csl > 1) em_cluster_sync(); else __syncthreads();
     }
 }
 
@@ -411,6 +508,7 @@ static int em_wave(vpk_ctx* ctx, EmState* st, EmParams& P, int n, int nmax) {
     if (P.stats) VPK_CUDA(cudaMemsetAsync(P.stats, 0, 4 * sizeof(unsigned long long), sm));
     P.n_slots = n;
     const int tiles = (nmax + kTK - 1) / kTK;
+    const int csl = wmat_split(nmax);         // cluster size of the W launches (slots use min(wmat_split(N), csl))
     if (P.cfg.use_weights) {
         KernelScope ks(ctx, "em_pair");
         em_pair_kernel<<<dim3(tiles, n), kPairThreads, 0, sm>>>(P);
@@ -439,7 +537,16 @@ static int em_wave(vpk_ctx* ctx, EmState* st, EmParams& P, int n, int nmax) {
             }
             {
                 KernelScope ks(ctx, "em_wmat");
-                em_wmat_kernel<<<dim3(tiles, bound), kWThreads, sizeof(WSmem), sm>>>(P, cur);
+                cudaLaunchConfig_t lc = {};
+                lc.gridDim = dim3(tiles * csl, bound);
+                lc.blockDim = dim3(kWThreads);
+                lc.dynamicSmemBytes = sizeof(WSmem);
+                lc.stream = sm;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = csl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                lc.attrs = at; lc.numAttrs = 1;
+                VPK_CUDA(cudaLaunchKernelEx(&lc, em_wmat_kernel, P, cur, csl));
                 VPK_TRY(check_launch("em_wmat"));
             }
             {

@@ -38,13 +38,14 @@ namespace em {
 #if !defined(__CUDACC__)
 using std::isinf;
 using std::isnan;
+inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 #endif
 
 constexpr int kMaxM = VPK_MAX_VP;
 constexpr int kMaxComp = 100;              // probability_functions.py:87
 constexpr int kCells = VPK_GRID * VPK_GRID;
 constexpr int kTK = 64;                    // columns per similarity slab (W kernel tile)
-constexpr int kMP = 16;                    // VP rows per weight-matrix pass
+constexpr int kMP = 32;                    // VP rows per weight-matrix pass (two groups of <= 16)
 constexpr int kPostThreads = 512;
 constexpr int kK1 = 10;                    // kNN rating: nearest by distance (vp_localisation.py:34)
 constexpr double kPi = 3.141592653589793;
@@ -123,7 +124,7 @@ struct EmSlot {
     unsigned long long ws_off;             // doubles from the workspace base
     double cur[kMaxM][3], nxt[kMaxM][3], s[kMaxM];
     // constants of the E-step on the selected VP set (prepare_estep)
-    double pv[kMaxM], vx[kMaxM], vy[kMaxM], two_s[kMaxM], coef[kMaxM];
+    double pv[kMaxM], vx[kMaxM], vy[kMaxM], inv2s[kMaxM], coef[kMaxM];
     double cw[kMaxM];
     int32_t cnt[kMaxM];
     double pdf_a[kMaxComp], pdf_b[kMaxComp], pdf_w[kMaxComp];
@@ -148,13 +149,27 @@ struct Img {
     double* lvsq;          // (kMaxM,N)  -- lvsq|pvl|w|wt are contiguous: split scratch
     double* pvl;           // (kMaxM,N)
     double* w;             // (kMaxM,N)
-    double* wt;            // (kMaxM/kMP, N, kMP): pvl*lweight, the A operand of the W kernel
+    double* wt;            // pvl*lweight, the A operand of the W kernel: pass p (VP rows 32p..32p+31) at
+                           // wt + p*N*32, line n of the pass at stride wpass_stride(M, p) (rows padded with zeros)
     size_t scratch_cap;    // doubles available from lvsq on
 };
 
 VPK_HD size_t lsim_doubles(int N) { return (size_t)((N + kTK - 1) / kTK) * kTK * (size_t)N; }
 VPK_HD size_t lsim_index(int N, int j, int k) { return ((size_t)(k / kTK) * N + j) * kTK + (k % kTK); }
-VPK_HD size_t wt_index(int N, int n, int m) { return ((size_t)(m / kMP) * N + n) * kMP + (m % kMP); }
+// Shape of pass p of the weight-matrix product for M hypotheses: G groups of warps, R VP rows per
+// thread (R in {4, 8, 12, 16}); the pass covers G*R >= rows-in-pass VP rows.
+VPK_HD void wpass_shape(int M, int p, int& G, int& R) {
+    int mp = M - p * kMP;
+    if (mp > kMP) mp = kMP;
+    G = mp > 16 ? 2 : 1;
+    R = ((mp + G - 1) / G + 3) & ~3;
+    if (R < 4) R = 4;
+}
+VPK_HD int wpass_stride(int M, int p) { int G, R; wpass_shape(M, p, G, R); return G * R; }
+VPK_HD size_t wt_index(int N, int n, int m, int M) {
+    const int p = m / kMP;
+    return (size_t)p * N * kMP + (size_t)n * wpass_stride(M, p) + (m % kMP);
+}
 VPK_HD size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 VPK_HD size_t slot_doubles(int N) {
@@ -228,17 +243,59 @@ VPK_DEV double proximity(const Seg& a, const Seg& b, double d) {
 // lines_similarity (:700-705)
 VPK_DEV double similarity(const Seg& a, const Seg& b, double d) { return cosangle(a, b, 9.0) * proximity(a, b, d); }
 
+// ---- the O(N^2) pair pass works on per-segment constants so that a pair costs no division or
+// square root: reciprocals are taken once per segment (results differ from the reference's
+// per-pair divisions by rounding only, ~1e-16 relative).
+struct SegPre { double x1, y1, x2, y2, dx, dy, inv_nn, inv_len, h; };
+VPK_DEV SegPre seg_pre(const Seg& s) {
+    SegPre p;
+    p.x1 = s.x1; p.y1 = s.y1; p.x2 = s.x2; p.y2 = s.y2;
+    p.dx = s.x2 - s.x1; p.dy = s.y2 - s.y1;
+    const double nrm = sqrt(p.dx * p.dx + p.dy * p.dy);
+    p.inv_nn = 1.0 / (nrm * nrm);          // line_segment_point_distance :747
+    p.inv_len = 1.0 / nrm;                 // lines_points_cosangle :719
+    p.h = 1.0 / (2 * nrm * nrm);           // lines_proximity :711 with sigma = 1
+    return p;
+}
+VPK_DEV double psd2_pre(const SegPre& s, double px, double py) {
+    const double param = ((px - s.x1) * s.dx + (py - s.y1) * s.dy) * s.inv_nn;
+    double cx, cy;
+    if (param < 0) { cx = s.x1; cy = s.y1; }
+    else if (param > 1) { cx = s.x2; cy = s.y2; }
+    else { cx = s.x1 + param * s.dx; cy = s.y1 + param * s.dy; }
+    const double ex = cx - px, ey = cy - py;
+    return ex * ex + ey * ey;
+}
+// squared closest distance of two segments (line_distance_closest :727-740)
+VPK_DEV double seg_distance2(const SegPre& a, const SegPre& b) {
+    return fmin(fmin(psd2_pre(a, b.x1, b.y1), psd2_pre(a, b.x2, b.y2)), fmin(psd2_pre(b, a.x1, a.y1), psd2_pre(b, a.x2, a.y2)));
+}
+// cos(clip(9 acos(c), +-pi/2)), c = |cos| of the angle between the segments (:715-724 with f = 9).
+// For 9 acos(c) >= pi/2 the reference evaluates cos(pi/2) = 6.123e-17; below that
+// cos(9 t) = T3(T3(cos t)) with T3(x) = 4x^3 - 3x (no acos / cos evaluation).
+VPK_DEV double cos9_pre(const SegPre& a, const SegPre& b) {
+    double c = fabs((a.dx * b.dx + a.dy * b.dy) * (a.inv_len * b.inv_len));
+    c = c > 1.0 ? 1.0 : c;                 // NaN stays NaN
+    if (c <= 0.984807753012208) return 6.123233995736766e-17;
+    const double t = c * (4.0 * c * c - 3.0);
+    const double r = t * (4.0 * t * t - 3.0);
+    return r < 6.123233995736766e-17 ? 6.123233995736766e-17 : r;
+}
+VPK_DEV double prox_pre(const SegPre& a, const SegPre& b, double d2) { return exp(-(d2 * fmax(a.h, b.h))); }
+// lines_similarity (:700-705) from the squared distance
+VPK_DEV double similarity_pre(const SegPre& a, const SegPre& b, double d2) { return cos9_pre(a, b) * prox_pre(a, b, d2); }
+
 // E4 tail (vp_localisation.py:50-72, :230-233): line score from the k1 nearest segments
-// cj/cd (ascending distance, ties by index; the line itself enters with distance 4, :82).
-VPK_DEVFN double rate_line(const double* lp, int i, const int* cj, const double* cd, int cnt, int N) {
+// cj/cd2 (ascending squared distance, ties by index; the line itself enters with distance 4, :82).
+VPK_DEVFN double rate_line(const double* lp, int i, const int* cj, const double* cd2, int cnt, int N) {
     const int k2 = imin(4, N);
-    const Seg si = load_seg(lp, i);
+    const SegPre si = seg_pre(load_seg(lp, i));
     double c[kK1], px[kK1];
     for (int q = 0; q < cnt; ++q) {
-        Seg sj = load_seg(lp, cj[q]);
-        double cc = cosangle(si, sj, 9.0);
-        double dtrue = (cj[q] == i) ? seg_distance(si, sj) : cd[q];       // :65 recomputes the true distance
-        px[q] = proximity(si, sj, dtrue);
+        const SegPre sj = seg_pre(load_seg(lp, cj[q]));
+        double cc = cos9_pre(si, sj);
+        double d2true = (cj[q] == i) ? seg_distance2(si, sj) : cd2[q];     // :65 recomputes the true distance
+        px[q] = prox_pre(si, sj, d2true);
         c[q] = isnan(cc) ? -INFINITY : cc;
     }
     // the k2 largest cosangles, descending; argsort()[::-1] puts the later of equal values first (:57-59)
@@ -253,7 +310,8 @@ VPK_DEVFN double rate_line(const double* lp, int i, const int* cj, const double*
     score /= (double)k2;
     double ls = fmin(fmax(score, 0.2), 1.0);      // :231
     if (isnan(score)) ls = score;
-    return seg_len(si) * ls;                      // :232-233
+    const Seg s0 = load_seg(lp, i);
+    return seg_len(s0) * ls;                      // :232-233
 }
 
 // insert (d, j) into an ascending candidate list of capacity kK1 (ties: smaller j first).
@@ -548,7 +606,7 @@ VPK_DEVFN void prepare_estep(EmSlot& st, const double (*v)[3], const Team& T) {
             double sm = st.s[m] > 1e-200 ? st.s[m] : 1e-200;    // calc_plv mutates s (:139)
             if (isnan(st.s[m])) sm = 1e-200;
             st.s[m] = sm;
-            st.two_s[m] = 2.0 * sm;
+            st.inv2s[m] = 1.0 / (2.0 * sm);
             st.coef[m] = 1.0 / sqrt(2.0 * kPi * sm);
         }
     }
@@ -556,47 +614,53 @@ VPK_DEVFN void prepare_estep(EmSlot& st, const double (*v)[3], const Team& T) {
 }
 
 // E5 part 2 (probability_functions.py:99-147).  Per-line constants of calc_lvsq_angle (:157-176):
-struct LineGeom { double mx, my, bx, by, nb; };
+struct LineGeom { double mx, my, bx, by, inv_nb; };
 VPK_DEV LineGeom line_geom(const double* lp, int n) {
     Seg sg = load_seg(lp, n);
     LineGeom g;
     g.mx = 0.5 * (sg.x1 + sg.x2); g.my = 0.5 * (sg.y1 + sg.y2);
     g.bx = sg.x1 - sg.x2; g.by = sg.y1 - sg.y2;
-    g.nb = sqrt(g.bx * g.bx + g.by * g.by);
+    g.inv_nb = 1.0 / sqrt(g.bx * g.bx + g.by * g.by);
     return g;
 }
-// one (line, VP) pair: lvsq (:174) and p(l|v) (calc_plv :140-145)
-VPK_DEV void estep_nm(const LineGeom& g, double vx, double vy, double two_s, double coef, double& lvsq, double& plv) {
+// one (line, VP) pair: lvsq (:174) and p(l|v) (calc_plv :140-145).  The divisions of the reference
+// are multiplications by reciprocals taken once per line / per VP (rounding-level difference).
+VPK_DEV void estep_nm(const LineGeom& g, double vx, double vy, double inv2s, double coef, double& lvsq, double& plv) {
     double ax = g.mx - vx, ay = g.my - vy;
-    double c = (ax * g.bx + ay * g.by) / (sqrt(ax * ax + ay * ay) * g.nb);
+    double c = (ax * g.bx + ay * g.by) * (rsqrt(ax * ax + ay * ay) * g.inv_nb);
     double q = 1.0 - fabs(c);
     lvsq = q * q;
-    plv = exp(-(lvsq / two_s)) * coef;
+    plv = exp(-(lvsq * inv2s)) * coef;
 }
 // whole line (host build): lvsq, p(v|l), and the W-kernel operand wt = p(v|l) * lweight
-VPK_DEV void estep_line(const Img& im, int M, const double* pv, const double* vx, const double* vy, const double* two_s,
+VPK_DEV void estep_line(const Img& im, int M, const double* pv, const double* vx, const double* vy, const double* inv2s,
                         const double* coef, int n) {
     const int N = im.N;
     const LineGeom g = line_geom(im.lp, n);
     double pl = 0.0;
     for (int m = 0; m < M; ++m) {
         double lvsq, plv;
-        estep_nm(g, vx[m], vy[m], two_s[m], coef[m], lvsq, plv);
+        estep_nm(g, vx[m], vy[m], inv2s[m], coef[m], lvsq, plv);
         im.lvsq[(size_t)m * N + n] = lvsq;
         im.pvl[(size_t)m * N + n] = plv;
         pl += plv * pv[m];
     }
     if (pl < 1e-12) pl = 1e-12;                                         // :117 (NaN stays NaN)
+    const double inv_pl = 1.0 / pl;
     const double lw = im.lweight[n];
-    const int mpad = ((M + kMP - 1) / kMP) * kMP;
-    for (int m = 0; m < mpad; ++m) {
-        double x = 0.0;
-        if (m < M) {
-            x = im.pvl[(size_t)m * N + n] * pv[m] / pl;                 // calc_pvl (:128)
-            im.pvl[(size_t)m * N + n] = x;
-            x *= lw;                                                    // weight_matrix :517
+    const int passes = (M + kMP - 1) / kMP;
+    for (int p = 0; p < passes; ++p) {
+        const int ws = wpass_stride(M, p);
+        for (int mm = 0; mm < ws; ++mm) {
+            const int m = p * kMP + mm;
+            double x = 0.0;
+            if (m < M) {
+                x = im.pvl[(size_t)m * N + n] * pv[m] * inv_pl;         // calc_pvl (:128)
+                im.pvl[(size_t)m * N + n] = x;
+                x *= lw;                                                // weight_matrix :517
+            }
+            im.wt[wt_index(N, n, m, M)] = x;
         }
-        im.wt[wt_index(N, n, m)] = x;
     }
 }
 
@@ -647,31 +711,54 @@ VPK_DEVFN void line_counts(const Img& im, EmSlot& st, double thresh, const Team&
     team_sync();
 }
 
-// E7 for one VP by one warp: smallest eigenvector of sum (w/max w)^2 l l^T over
-// the selected lines.  sel < 0: all lines; sel >= 0: only lines with assoc == sel
-// (final refit).  wrow2: optional second weight row added to the first (merge).
-VPK_DEVFN bool refit_vp(const Img& im, const double* wrow, const double* wrow2, int sel, double out[3], const Team& T) {
+// E7 + E8 for one VP by one warp.
+// E7: smallest eigenvector of sum (w/max w)^2 l l^T over the selected lines (sel < 0: all lines;
+// sel >= 0: only lines with assoc == sel, the final refit).  wrow2: optional second weight row
+// added to the first (merge).  Returns false where calc_new_vanishing_point returns None.
+// E8: *s_out = exp(log(sum lvsq*pvl) - log(sum pvl)) over ALL lines for VP row vm
+// (vp_localisation.py:301-304), or the pooled form of merge_vps (:663-664) if vm2 >= 0.
+// Two sweeps over the lines: the row maximum, then every sum at once.
+VPK_DEVFN bool refit_vp(const Img& im, const double* wrow, const double* wrow2, int sel, int vm, int vm2, double out[3],
+                        double* s_out, const Team& T) {
     const int N = im.N;
     double mx = -INFINITY;
     bool any = false;
+#pragma unroll 4
     for (int n = T.lane; n < N; n += T.lanes) {
-        if (sel >= 0 && im.assoc[n] != sel) continue;
-        double x = wrow[n] + (wrow2 ? wrow2[n] : 0.0);
-        any = true;
-        mx = nanmax(mx, x);
+        const double x = wrow[n] + (wrow2 ? wrow2[n] : 0.0);
+        const bool use = sel < 0 || im.assoc[n] == sel;
+        if (use) { any = true; mx = nanmax(mx, x); }
     }
     mx = warp_max_nanprop(mx);
     any = warp_any(any);
-    if (!any || mx == 0.0 || isnan(mx) || isinf(mx)) return false;      // :456-460 / LinAlgError
+    const bool fit = !(!any || mx == 0.0 || isnan(mx) || isinf(mx));     // :456-460 / LinAlgError
+    const double* p1 = im.pvl + (size_t)vm * N;
+    const double* q1 = im.lvsq + (size_t)vm * N;
+    const double* p2 = vm2 >= 0 ? im.pvl + (size_t)vm2 * N : nullptr;
+    const double* q2 = vm2 >= 0 ? im.lvsq + (size_t)vm2 * N : nullptr;
     double g[6] = {0, 0, 0, 0, 0, 0};
+    double num = 0.0, den = 0.0;
     int rows = 0, only = -1;
+#pragma unroll 4
     for (int n = T.lane; n < N; n += T.lanes) {
-        if (sel >= 0 && im.assoc[n] != sel) continue;
-        double x = (wrow[n] + (wrow2 ? wrow2[n] : 0.0)) / mx;
-        double a = x * im.ln[3 * (size_t)n], b = x * im.ln[3 * (size_t)n + 1], c = x * im.ln[3 * (size_t)n + 2];
-        g[0] += a * a; g[1] += a * b; g[2] += a * c; g[3] += b * b; g[4] += b * c; g[5] += c * c;
-        ++rows; only = n;
+        double p = p1[n], q = q1[n];
+        if (p2) { p += p2[n]; q = 0.5 * (q2[n] + q); }
+        num += q * p;
+        den += p;
+        const double wv = wrow[n] + (wrow2 ? wrow2[n] : 0.0);
+        const double l0 = im.ln[3 * (size_t)n], l1 = im.ln[3 * (size_t)n + 1], l2 = im.ln[3 * (size_t)n + 2];
+        const bool use = fit && (sel < 0 || im.assoc[n] == sel);
+        if (use) {
+            const double x = wv / mx;
+            const double a = x * l0, b = x * l1, c = x * l2;
+            g[0] += a * a; g[1] += a * b; g[2] += a * c; g[3] += b * b; g[4] += b * c; g[5] += c * c;
+            ++rows; only = n;
+        }
     }
+    num = warp_sum(num);
+    den = warp_sum(den);
+    *s_out = exp(log(num) - log(den));
+    if (!fit) return false;
 #pragma unroll
     for (int k = 0; k < 6; ++k) g[k] = warp_sum(g[k]);
     rows = warp_sum_i(rows);
@@ -699,22 +786,6 @@ VPK_DEVFN bool refit_vp(const Img& im, const double* wrow, const double* wrow2, 
     double sg = sign_np(e[2]);                                           // :474
     out[0] = e[0] * sg; out[1] = e[1] * sg; out[2] = e[2] * sg;
     return true;
-}
-
-// s = exp(log(sum lvsq*pvl) - log(sum pvl))   (vp_localisation.py:301-304), one warp
-VPK_DEVFN double variance_update(const Img& im, int m, int m2, const Team& T) {
-    const int N = im.N;
-    double num = 0.0, den = 0.0;
-    for (int n = T.lane; n < N; n += T.lanes) {
-        double p = im.pvl[(size_t)m * N + n];
-        double q = im.lvsq[(size_t)m * N + n];
-        if (m2 >= 0) { p += im.pvl[(size_t)m2 * N + n]; q = 0.5 * (im.lvsq[(size_t)m2 * N + n] + q); }   // merge (:663-664)
-        num += q * p;
-        den += p;
-    }
-    num = warp_sum(num);
-    den = warp_sum(den);
-    return exp(log(num) - log(den));
 }
 
 // remove the VPs flagged in rem[] from cur / nxt / s (numpy.delete along the VP axis)
@@ -1085,8 +1156,8 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
                     continue;
                 }
                 double nv[3];
-                bool okv = refit_vp(im, im.w + (size_t)m * N, nullptr, -1, nv, T);
-                double sv = okv ? variance_update(im, m, -1, T) : 0.0;
+                double sv = 0.0;
+                bool okv = refit_vp(im, im.w + (size_t)m * N, nullptr, -1, m, -1, nv, &sv, T);
                 if (T.lane == 0) {
                     int rem = 0;
                     double err = 0.0;
@@ -1184,8 +1255,8 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
             const int j = st.merge_j, k = st.merge_k, M = st.M;
             if (T.warp == 0) {
                 double nv[3];
-                bool okv = refit_vp(im, im.w + (size_t)j * N, im.w + (size_t)k * N, -1, nv, T);
-                double sk = variance_update(im, k, j, T);
+                double sk = 0.0;
+                bool okv = refit_vp(im, im.w + (size_t)j * N, im.w + (size_t)k * N, -1, k, j, nv, &sk, T);
                 if (T.lane == 0) {
                     st.s[k] = sk;                                  // assigned before the test (:666)
                     sc.flag = (okv && !(sk > 0.01)) ? 1 : 0;       // max_stdd = 0.01 (:633, :668)
@@ -1222,8 +1293,8 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
                 have = warp_any(have);
                 if (!have) { if (T.lane == 0) sc.rem[m] = 0; continue; }
                 double nv[3];
-                bool okv = refit_vp(im, im.w + (size_t)m * N, nullptr, m, nv, T);
-                double sv = okv ? variance_update(im, m, -1, T) : 0.0;
+                double sv = 0.0;
+                bool okv = refit_vp(im, im.w + (size_t)m * N, nullptr, m, m, -1, nv, &sv, T);
                 if (T.lane == 0) {
                     int rem = 0;
                     if (!okv) rem = 1;
