@@ -113,38 +113,92 @@ __global__ void conv1_operand_kernel(const uint8_t* __restrict__ img, const floa
 }
 
 // Fused LRN (ACROSS_CHANNELS, size 5, alpha 1e-4, beta 0.75, k 1) + 3x3/2 ceil-mode max
-// pool (Caffe).  in: NHWC (n,H,W,C) bf16.  out: (n, Ho+2*opad, Wo+2*opad, Cout) with
-// channel c stored at (c / cg) * cgp + c % cg  (group padding of the next convolution).
-__global__ void lrn_pool_kernel(const __nv_bfloat16* __restrict__ in, int n_images, int H, int W, int C, int do_lrn,
-                                int Ho, int Wo, int opad, int Cout, int cg, int cgp, __nv_bfloat16* __restrict__ out) {
-    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    long long total = (long long)n_images * Ho * Wo * C;
-    if (t >= total) return;
-    int c = (int)(t % C);
-    long long r = t / C;
-    int ox = (int)(r % Wo); r /= Wo;
-    int oy = (int)(r % Ho);
-    int n = (int)(r / Ho);
-    int y0 = oy * 2, x0 = ox * 2, y1 = min(y0 + 3, H), x1 = min(x0 + 3, W);
-    float best = -INFINITY;
-    for (int y = y0; y < y1; ++y)
-        for (int x = x0; x < x1; ++x) {
-            const __nv_bfloat16* p = in + (((long long)n * H + y) * W + x) * C;
-            float v = __bfloat162float(p[c]);
-            if (do_lrn) {
-                float ss = 0.f;
+// pool (Caffe).  in: NHWC (n,H,W,C) bf16, C % 8 == 0.  out: (n, Ho+2*opad, Wo+2*opad, Cout)
+// with channel c stored at (c / cg) * cgp + c % cg  (group padding of the next convolution;
+// cg % 8 == 0).
+// One thread owns 8 channels of a 2x2 block of output pixels: it walks the 5x5 input
+// patch once (16-byte loads + two 4-byte channel-halo loads per pixel), normalises each
+// pixel once and folds it into the up to four windows it belongs to.
+__device__ __forceinline__ void bf16x8_to_float(const uint4& v, float f[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
-                for (int d = -2; d <= 2; ++d) {
-                    int cc = c + d;
-                    if (cc >= 0 && cc < C) { float u = __bfloat162float(p[cc]); ss += u * u; }
+    for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+
+template <bool kLrn>
+__global__ void __launch_bounds__(256) lrn_pool_kernel(const __nv_bfloat16* __restrict__ in, int n_images, int H, int W, int C,
+                                                       int Ho, int Wo, int opad, int Cout, int cg, int cgp,
+                                                       __nv_bfloat16* __restrict__ out) {
+    const int CG = C >> 3, Hb = (Ho + 1) >> 1, Wb = (Wo + 1) >> 1;
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long total = (long long)n_images * Hb * Wb * CG;
+    if (t >= total) return;
+    const int g = (int)(t % CG);
+    long long r = t / CG;
+    const int bx = (int)(r % Wb); r /= Wb;
+    const int by = (int)(r % Hb);
+    const int n = (int)(r / Hb);
+    const int c0 = g * 8;
+    const int oy0 = by * 2, ox0 = bx * 2;
+    const int y0 = oy0 * 2, x0 = ox0 * 2;
+    float best[2][2][8];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) best[a][b][k] = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 5; ++dy) {
+        const int y = y0 + dy;
+        if (y >= H) break;
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) {
+            const int x = x0 + dx;
+            if (x >= W) break;
+            const __nv_bfloat16* p = in + (((long long)n * H + y) * W + x) * C + c0;
+            float v[8];
+            bf16x8_to_float(*reinterpret_cast<const uint4*>(p), v);
+            if (kLrn) {
+                float lo0 = 0.f, lo1 = 0.f, hi0 = 0.f, hi1 = 0.f;
+                if (c0 > 0) { float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p - 2)); lo0 = q.x; lo1 = q.y; }
+                if (c0 + 8 < C) { float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p + 8)); hi0 = q.x; hi1 = q.y; }
+                float sq[12];
+                sq[0] = lo0 * lo0; sq[1] = lo1 * lo1; sq[10] = hi0 * hi0; sq[11] = hi1 * hi1;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) sq[2 + k] = v[k] * v[k];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float ss = sq[k] + sq[k + 1] + sq[k + 2] + sq[k + 3] + sq[k + 4];
+                    v[k] = v[k] * __powf(1.f + (1e-4f / 5.f) * ss, -0.75f);
                 }
-                v = v * __powf(1.f + (1e-4f / 5.f) * ss, -0.75f);
             }
-            best = fmaxf(best, v);
+            // rows dy 0..2 feed output row 0, rows 2..4 output row 1 (same for columns)
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+                    if (dy >= 2 * a && dy <= 2 * a + 2 && dx >= 2 * b && dx <= 2 * b + 2) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) best[a][b][k] = fmaxf(best[a][b][k], v[k]);
+                    }
         }
-    int Hop = Ho + 2 * opad, Wop = Wo + 2 * opad;
-    int co = (c / cg) * cgp + (c % cg);
-    out[(((long long)n * Hop + oy + opad) * Wop + ox + opad) * Cout + co] = __float2bfloat16_rn(best);
+    }
+    const int Hop = Ho + 2 * opad, Wop = Wo + 2 * opad;
+    const int co = (c0 / cg) * cgp + (c0 % cg);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int oy = oy0 + a, ox = ox0 + b;
+            if (oy < Ho && ox < Wo) {
+                uint4 o;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(best[a][b][2 * i], best[a][b][2 * i + 1]);
+                *reinterpret_cast<uint4*>(out + (((long long)n * Hop + oy + opad) * Wop + ox + opad) * Cout + co) = o;
+            }
+        }
 }
 
 __global__ void sigmoid_kernel(const float* __restrict__ x, long long n, float* __restrict__ y) {
@@ -281,8 +335,8 @@ int cnn_forward_dev(vpk_ctx* ctx, const uint8_t* d_images, int32_t n, float* d_s
     VPK_TRY(launch_gemm(ctx, c));
     {
         KernelScope ks(ctx, "lrn_pool1");
-        long long t = (long long)n * 61 * 61 * 96;
-        lrn_pool_kernel<<<(unsigned)((t + 255) / 256), 256, 0, ctx->stream>>>(s->c1.as<bf>(), n, 123, 123, 96, 1, 61, 61, 2, 128, 48, 64, s->a2.as<bf>());
+        long long t = (long long)n * 31 * 31 * 12;
+        lrn_pool_kernel<true><<<(unsigned)((t + 255) / 256), 256, 0, ctx->stream>>>(s->c1.as<bf>(), n, 123, 123, 96, 61, 61, 2, 128, 48, 64, s->a2.as<bf>());
         VPK_TRY(check_launch("lrn_pool1"));
     }
     // conv2: 5x5 pad 2, 2 groups of 48 (stored as 64) -> 128 each
@@ -296,8 +350,8 @@ int cnn_forward_dev(vpk_ctx* ctx, const uint8_t* d_images, int32_t n, float* d_s
     VPK_TRY(launch_gemm(ctx, c));
     {
         KernelScope ks(ctx, "lrn_pool2");
-        long long t = (long long)n * 30 * 30 * 256;
-        lrn_pool_kernel<<<(unsigned)((t + 255) / 256), 256, 0, ctx->stream>>>(s->c2.as<bf>(), n, 61, 61, 256, 1, 30, 30, 1, 256, 256, 256, s->a3.as<bf>());
+        long long t = (long long)n * 15 * 15 * 32;
+        lrn_pool_kernel<true><<<(unsigned)((t + 255) / 256), 256, 0, ctx->stream>>>(s->c2.as<bf>(), n, 61, 61, 256, 30, 30, 1, 256, 256, 256, s->a3.as<bf>());
         VPK_TRY(check_launch("lrn_pool2"));
     }
     // conv3: 3x3 pad 1, 256 -> 384, written into conv4's padded input
@@ -329,8 +383,8 @@ int cnn_forward_dev(vpk_ctx* ctx, const uint8_t* d_images, int32_t n, float* d_s
     VPK_TRY(launch_gemm(ctx, c));
     {
         KernelScope ks(ctx, "pool5");
-        long long t = (long long)n * 15 * 15 * 256;
-        lrn_pool_kernel<<<(unsigned)((t + 255) / 256), 256, 0, ctx->stream>>>(s->c5.as<bf>(), n, 30, 30, 256, 0, 15, 15, 0, 256, 256, 256, s->a6.as<bf>());
+        long long t = (long long)n * 8 * 8 * 32;
+        lrn_pool_kernel<false><<<(unsigned)((t + 255) / 256), 256, 0, ctx->stream>>>(s->c5.as<bf>(), n, 30, 30, 256, 15, 15, 0, 256, 256, 256, s->a6.as<bf>());
         VPK_TRY(check_launch("pool5"));
     }
     // fc6 / fc7 / fc8

@@ -292,7 +292,8 @@ struct WSmem {
     unsigned long long full[kStages], empty[kStages];
 };
 
-__host__ __device__ inline int wmat_split(int N) { return N <= 384 ? 1 : (N <= 768 ? 2 : (N <= 1536 ? 4 : 8)); }
+// CTAs per slab: only very tall slabs are split (the cluster barriers cost ~20 % of a short CTA's time)
+__host__ __device__ inline int wmat_split(int N) { return N <= 1536 ? 1 : (N <= 3072 ? 2 : 4); }
 
 __device__ __forceinline__ void em_mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -358,19 +359,31 @@ __device__ __forceinline__ void wmat_pass(WSmem& sm, const double* slab, const d
         }
         em_mbar_wait(em_smem_u32(&sm.full[s]), (uint32_t)((pos / kStages) & 1));
         const int jn = min(kJR, N - (c0 + i) * kJR);
-        for (int rr = 0; rr < rpw; ++rr) {
-            const int r = wg * rpw + rr;
-            if (r < jn) {
-                const double2 a2 = *reinterpret_cast<const double2*>(&sm.a[s][r * kTK + 2 * lane]);
-                const double2* b2 = reinterpret_cast<const double2*>(&sm.b[s][r * ws + g * R]);
+        auto row_fma = [&](int r) {
+            const double2 a2 = *reinterpret_cast<const double2*>(&sm.a[s][r * kTK + 2 * lane]);
+            const double2* b2 = reinterpret_cast<const double2*>(&sm.b[s][r * ws + g * R]);
 #pragma unroll
-                for (int q = 0; q < R / 2; ++q) {
-                    const double2 bb = b2[q];
-                    acc[2 * q][0] = fma(bb.x, a2.x, acc[2 * q][0]);
-                    acc[2 * q][1] = fma(bb.x, a2.y, acc[2 * q][1]);
-                    acc[2 * q + 1][0] = fma(bb.y, a2.x, acc[2 * q + 1][0]);
-                    acc[2 * q + 1][1] = fma(bb.y, a2.y, acc[2 * q + 1][1]);
-                }
+            for (int q = 0; q < R / 2; ++q) {
+                const double2 bb = b2[q];
+                acc[2 * q][0] = fma(bb.x, a2.x, acc[2 * q][0]);
+                acc[2 * q][1] = fma(bb.x, a2.y, acc[2 * q][1]);
+                acc[2 * q + 1][0] = fma(bb.y, a2.x, acc[2 * q + 1][0]);
+                acc[2 * q + 1][1] = fma(bb.y, a2.y, acc[2 * q + 1][1]);
+            }
+        };
+        if (jn == kJR) {
+            // full chunk: no per-row predicate, so the loads of the next row can be hoisted over the FMAs
+            if (G == 1) {
+#pragma unroll
+                for (int rr = 0; rr < kJR / NWARP; ++rr) row_fma(wg * (kJR / NWARP) + rr);
+            } else {
+#pragma unroll
+                for (int rr = 0; rr < 2 * kJR / NWARP; ++rr) row_fma(wg * (2 * kJR / NWARP) + rr);
+            }
+        } else {
+            for (int rr = 0; rr < rpw; ++rr) {
+                const int r = wg * rpw + rr;
+                if (r < jn) row_fma(r);
             }
         }
         __syncwarp();

@@ -391,9 +391,14 @@ VPK_DEVFN bool smallest_eigvec3(const double g[6], double out[3]) {
 // ---------------------------------------------------------------------------
 // scratch of the per-slot kernels (shared memory on the device)
 // ---------------------------------------------------------------------------
+constexpr int kLinkMax = 640;              // clusterings up to this size keep their bookkeeping in shared memory
 struct PostScratch {
     double redv[kPostThreads];
     int redi[kPostThreads], redj[kPostThreads];
+    // average-linkage bookkeeping (split_best_vp)
+    double l_rmin[kLinkMax], l_csize[kLinkMax];
+    int l_rarg[kLinkMax], l_nodeid[kLinkMax], l_rep[kLinkMax], l_flist[kLinkMax];
+    int l_nflag;
     double ang[kMaxM], err[kMaxM], nv[kMaxM][3];
     int ok[kMaxM], rem[kMaxM];
     int ia, ib, flag;
@@ -814,31 +819,39 @@ VPK_DEVFN void compact_vps(EmSlot& st, const int* rem, const Team& T) {
 // complete connectivity graph); labels follow _hc_cut: label 0 = the root's
 // child with the larger node id.
 VPK_DEVFN void average_linkage_two(double* D, int n, int* rep, int* nodeid, double* csize, double* rmin, int* rarg,
-                                    int* need, PostScratch& sc, const Team& T) {
+                                    int* flist, PostScratch& sc, const Team& T) {
     // rmin[a] / rarg[a]: the first minimum of row a over the active columns b > a.  The global
     // minimum over active pairs a < b with lexicographic tie-break is then the smallest rmin, ties
-    // to the smallest a.  After a merge only the rows whose cached minimum involved the merged
-    // pair are rescanned.
+    // to the smallest a.  After a merge the new row's minimum falls out of the update itself and
+    // only the rows whose cached minimum involved the merged pair are rescanned (flist).
     const int tid = T.tid, NT = T.nthreads;
-    for (int i = tid; i < n; i += NT) { rep[i] = i; nodeid[i] = i; csize[i] = 1.0; need[i] = 1; }
+    for (int i = tid; i < n; i += NT) { rep[i] = i; nodeid[i] = i; csize[i] = 1.0; flist[i] = i; }
+    if (tid == 0) sc.l_nflag = n;
     team_sync();
-    for (int step = 0; step < n - 1; ++step) {
-        // (re)scan the flagged rows, one warp per row
-        for (int a = T.warp; a < n; a += T.nwarps) {
-            if (nodeid[a] < 0 || !need[a]) continue;
+    for (int step = 0; step < n - 2; ++step) {
+        // rescan the flagged rows, one warp per row
+        const int nflag = sc.l_nflag;
+        for (int f = T.warp; f < nflag; f += T.nwarps) {
+            const int a = flist[f];
             double bd = INFINITY;
             int bb = -1;
             const double* row = D + (size_t)a * n;
-            for (int b = a + 1 + T.lane; b < n; b += T.lanes) {
-                if (nodeid[b] < 0) continue;
-                double d = row[b];
-                if (bb < 0 || d < bd) { bd = d; bb = b; }
+            // 8 independent loads per lane in flight (one memory round trip per 256 columns)
+            for (int b0 = a + 1 + T.lane; b0 < n; b0 += 8 * T.lanes) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int b = b0 + u * T.lanes; v[u] = b < n ? row[b] : INFINITY; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int b = b0 + u * T.lanes;
+                    if (b < n && nodeid[b] >= 0 && (bb < 0 || v[u] < bd)) { bd = v[u]; bb = b; }
+                }
             }
             warp_min_pair(bd, bb);
-            if (T.lane == 0) { rmin[a] = bd; rarg[a] = bb; need[a] = 0; }
+            if (T.lane == 0) { rmin[a] = bd; rarg[a] = bb; }
         }
         team_sync();
-        if (step == n - 2) break;
+        if (tid == 0) sc.l_nflag = 0;
         double bd = INFINITY;
         int ba = -1;
         for (int a = tid; a < n; a += NT) {
@@ -852,21 +865,38 @@ VPK_DEVFN void average_linkage_two(double* D, int n, int* rep, int* nodeid, doub
         const int b = rarg[a];
         const double na = csize[a], nb = csize[b];
         team_sync();
+        // new distances of the merged cluster (kept at index a); its own row minimum on the fly
+        double ad = INFINITY;
+        int ac = -1;
         for (int c = tid; c < n; c += NT) {
             if (c == a || c == b || nodeid[c] < 0) continue;
             double dn = (na * D[(size_t)a * n + c] + nb * D[(size_t)b * n + c]) / (na + nb);   // average_merge
             D[(size_t)a * n + c] = dn;
             D[(size_t)c * n + a] = dn;
             if (c < a) {
-                if (rarg[c] == a || rarg[c] == b) need[c] = 1;
+                if (rarg[c] == a || rarg[c] == b) {
+#if defined(__CUDACC__)
+                    flist[atomicAdd(&sc.l_nflag, 1)] = c;
+#else
+                    flist[sc.l_nflag++] = c;
+#endif
+                }
                 else if (dn < rmin[c] || (dn == rmin[c] && a < rarg[c])) { rmin[c] = dn; rarg[c] = a; }
-            } else if (c < b) {
-                if (rarg[c] == b) need[c] = 1;
+            } else {
+                if (c < b && rarg[c] == b) {
+#if defined(__CUDACC__)
+                    flist[atomicAdd(&sc.l_nflag, 1)] = c;
+#else
+                    flist[sc.l_nflag++] = c;
+#endif
+                }
+                if (ac < 0 || dn < ad) { ad = dn; ac = c; }
             }
         }
         for (int i = tid; i < n; i += NT)
             if (rep[i] == b) rep[i] = a;
-        if (tid == 0) { csize[a] = na + nb; nodeid[a] = n + step; nodeid[b] = -1; need[a] = 1; }
+        team_min_pair(ad, ac, sc, T);
+        if (tid == 0) { csize[a] = na + nb; nodeid[a] = n + step; nodeid[b] = -1; rmin[a] = sc.da; rarg[a] = sc.ia; }
         team_sync();
     }
     // the two survivors; label 0 = larger node id
@@ -953,7 +983,8 @@ VPK_DEVFN int split_best_vp(const Img& im, EmSlot& st, PostScratch& sc, double m
     const int worst = sc.ia;
     if (worst < 0) return -1;
     const int nw = st.cnt[worst];
-    // scratch layout (doubles): D[nw*nw] | csize[nw] | rmin[nw] | ints: idx rep nodeid rarg flag [nw each]
+    // scratch layout (doubles): D[nw*nw] | csize[nw] | rmin[nw] | ints: idx rep nodeid rarg flist [nw each]
+    // (the bookkeeping arrays live in shared memory when nw <= kLinkMax)
     size_t need = (size_t)nw * nw + 2 * (size_t)nw + (5 * (size_t)nw + 1) / 2 + 4;
     double* scratch = im.lvsq;
     bool locked = false;
@@ -977,6 +1008,9 @@ VPK_DEVFN int split_best_vp(const Img& im, EmSlot& st, PostScratch& sc, double m
     int* nodeid = rep + nw;
     int* rarg = nodeid + nw;
     int* rflag = rarg + nw;
+    if (nw <= kLinkMax) {
+        csize = sc.l_csize; rmin = sc.l_rmin; rep = sc.l_rep; nodeid = sc.l_nodeid; rarg = sc.l_rarg; rflag = sc.l_flist;
+    }
     if (tid == 0) {
         int k = 0;
         for (int n = 0; n < N; ++n) if (im.assoc[n] == worst) idx[k++] = n;
