@@ -65,9 +65,9 @@ class ClockSampler(threading.Thread):
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.02):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.period = index, [], False, period
         self.nv = self.h = None
         try:
             import pynvml
@@ -110,7 +110,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(parts)
             except Exception:
                 pass
-            time.sleep(0.02 if self.nv else 0.2)
+            time.sleep(self.period if self.nv else max(self.period, 0.2))
 
     def summary(self):
         self.stop_flag = True
@@ -232,7 +232,7 @@ def run_ours(args, rank, world, local_rank):
     pipe.upload(seg_pin.numpy(), off_pin.numpy())
     for _ in range(args.warmup):
         pipe.run()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.clock_period)
     sampler.start()
     barrier()
     launches0 = ctx.launch_count()
@@ -387,6 +387,7 @@ def main():
                     help="multiplier on the train_val.prototxt filler std (1.0 = the prototxt's own)")
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-period", type=float, default=0.02, help="seconds between NVML clock samples in the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))

@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(kPostThreads) em_post_kernel(EmParams P, int c
 struct EmState {
     DBuf ws, slots, desc, lists, ctl, stats, overflow, resp, out_small, out_assoc, out_dm, init_vp, init_off, sphere;
     HBuf h_desc, h_cnt;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool attr_set = false;
     unsigned long long totals[4] = {0, 0, 0, 0};   // accumulated W-product statistics + supersteps (profiling runs)
 };
@@ -535,10 +535,11 @@ static int em_wave(vpk_ctx* ctx, EmState* st, EmParams& P, int n, int nmax) {
     int* h_cnt = st->h_cnt.as<int>();
     int bound = n;              // upper bound of the number of active slots (they only ever finish)
     int step = 0;
+    static const int LA = getenv("VPK_EM_LOOKAHEAD") ? atoi(getenv("VPK_EM_LOOKAHEAD")) : 3;
     for (int chunk = 0;; ++chunk) {
-        if (chunk >= 2) {
-            VPK_CUDA(cudaEventSynchronize(st->ev[(chunk - 2) & 3]));
-            bound = h_cnt[(chunk - 2) & 3];
+        if (chunk >= LA) {
+            VPK_CUDA(cudaEventSynchronize(st->ev[(chunk - LA) & 7]));
+            bound = h_cnt[(chunk - LA) & 7];
             if (bound <= 0) break;
         }
         for (int k = 0; k < kChunkSteps; ++k, ++step) {
@@ -569,8 +570,8 @@ static int em_wave(vpk_ctx* ctx, EmState* st, EmParams& P, int n, int nmax) {
             }
         }
         // length of the list the next superstep will read
-        VPK_CUDA(cudaMemcpyAsync(h_cnt + (chunk & 3), P.ctl + (step & 1), sizeof(int), cudaMemcpyDeviceToHost, sm));
-        VPK_CUDA(cudaEventRecord(st->ev[chunk & 3], sm));
+        VPK_CUDA(cudaMemcpyAsync(h_cnt + (chunk & 7), P.ctl + (step & 1), sizeof(int), cudaMemcpyDeviceToHost, sm));
+        VPK_CUDA(cudaEventRecord(st->ev[chunk & 7], sm));
         if (step > 64 * (P.cfg.num_iter + 8)) { set_error("vpk_em: supersteps did not terminate"); return VPK_ERR_STATE; }
     }
     VPK_CUDA(cudaStreamSynchronize(sm));
@@ -605,7 +606,7 @@ int em_dev(vpk_ctx* ctx, const double* d_lines, const double* d_segments, const 
     size_t free_b = 0, total_b = 0;
     VPK_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const size_t budget = std::max<size_t>((free_b + st->ws.cap) / 2, (size_t)1 << 28) / sizeof(double);
-    VPK_TRY(st->h_cnt.ensure(4 * sizeof(int)));
+    VPK_TRY(st->h_cnt.ensure(8 * sizeof(int)));
     VPK_TRY(st->ctl.ensure(4 * sizeof(int)));
     VPK_TRY(st->stats.ensure(4 * sizeof(unsigned long long)));
 
@@ -636,7 +637,7 @@ int em_dev(vpk_ctx* ctx, const double* d_lines, const double* d_segments, const 
         VPK_TRY(st->slots.ensure(sizeof(EmSlot) * (size_t)n));
         VPK_TRY(st->desc.ensure(sizeof(SlotDesc) * (size_t)n));
         VPK_TRY(st->lists.ensure(2 * sizeof(int) * (size_t)n));
-        const size_t ov = (size_t)nmax * nmax + 4 * (size_t)nmax + 16;
+        const size_t ov = (size_t)nmax * nmax + 6 * (size_t)nmax + 16;
         VPK_TRY(st->overflow.ensure(ov * sizeof(double)));
         VPK_TRY(st->h_desc.ensure(sizeof(SlotDesc) * (size_t)n));
         SlotDesc* hd = st->h_desc.as<SlotDesc>();

@@ -91,6 +91,12 @@ VPK_DEV long long warp_sum_ll(long long v) {
     return v;
 }
 VPK_DEV bool warp_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+// number of lanes below this one with p set; total = lanes with p set
+VPK_DEV int warp_rank(bool p, int& total) {
+    const unsigned m = __ballot_sync(0xffffffffu, p);
+    total = __popc(m);
+    return __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+}
 // max that propagates NaN like numpy.max
 VPK_DEV double warp_max_nanprop(double v) {
     for (int o = 16; o > 0; o >>= 1) {
@@ -107,6 +113,7 @@ inline int warp_sum_i(int v) { return v; }
 inline int warp_max_i(int v) { return v; }
 inline long long warp_sum_ll(long long v) { return v; }
 inline bool warp_any(bool p) { return p; }
+inline int warp_rank(bool p, int& total) { total = p ? 1 : 0; return 0; }
 inline double warp_max_nanprop(double v) { return v; }
 #endif
 
@@ -391,13 +398,13 @@ VPK_DEVFN bool smallest_eigvec3(const double g[6], double out[3]) {
 // ---------------------------------------------------------------------------
 // scratch of the per-slot kernels (shared memory on the device)
 // ---------------------------------------------------------------------------
-constexpr int kLinkMax = 640;              // clusterings up to this size keep their bookkeeping in shared memory
+constexpr int kLinkMax = 512;              // clusterings up to this size keep their bookkeeping in shared memory
 struct PostScratch {
     double redv[kPostThreads];
     int redi[kPostThreads], redj[kPostThreads];
     // average-linkage bookkeeping (split_best_vp)
-    double l_rmin[kLinkMax], l_csize[kLinkMax];
-    int l_rarg[kLinkMax], l_nodeid[kLinkMax], l_rep[kLinkMax], l_flist[kLinkMax];
+    double l_nnd[kLinkMax], l_csize[kLinkMax], l_height[kLinkMax];
+    int l_nn[kLinkMax], l_mate[kLinkMax], l_rep[kLinkMax], l_act[kLinkMax], l_keep[kLinkMax / 2];
     int l_nflag;
     double ang[kMaxM], err[kMaxM], nv[kMaxM][3];
     int ok[kMaxM], rem[kMaxM];
@@ -814,101 +821,130 @@ VPK_DEVFN void compact_vps(EmSlot& st, const int* rem, const Team& T) {
 // ---------------------------------------------------------------------------
 // E11: split_best_vp (vp_localisation.py:527-630)
 // ---------------------------------------------------------------------------
-// UPGMA down to two clusters on the n x n matrix D (what scikit-learn's
-// AgglomerativeClustering(linkage='average', n_clusters=2) computes on a
-// complete connectivity graph); labels follow _hc_cut: label 0 = the root's
-// child with the larger node id.
-VPK_DEVFN void average_linkage_two(double* D, int n, int* rep, int* nodeid, double* csize, double* rmin, int* rarg,
-                                    int* flist, PostScratch& sc, const Team& T) {
-    // rmin[a] / rarg[a]: the first minimum of row a over the active columns b > a.  The global
-    // minimum over active pairs a < b with lexicographic tie-break is then the smallest rmin, ties
-    // to the smallest a.  After a merge the new row's minimum falls out of the update itself and
-    // only the rows whose cached minimum involved the merged pair are rescanned (flist).
+// UPGMA (average linkage) down to two clusters on the n x n matrix D -- what
+// scikit-learn's AgglomerativeClustering(linkage='average', n_clusters=2)
+// computes on a complete connectivity graph.  The dendrogram is built by rounds
+// of *reciprocal nearest neighbour* merges instead of one merge at a time:
+// average linkage is reducible, so every pair of clusters that are each other's
+// nearest neighbour is a node of the UPGMA tree and all such pairs can be merged
+// in the same round (Lance-Williams update in the order the sequential
+// algorithm would apply it, so only rounding-level differences).  A round never
+// takes the count below two, and the two survivors are the children of the
+// root.  ~log(n) rounds of block-wide work replace n - 2 dependent merges.
+// Ties: nearest neighbour under the total order (distance, smaller index, larger
+// index), which keeps the globally closest pair reciprocal (progress).
+// Labels follow _hc_cut: label 0 = the root's child with the larger node id,
+// i.e. the one formed later = with the larger merge height (a leaf: its index).
+VPK_DEVFN void average_linkage_two(double* D, int n, int* rep, int* mate, double* csize, double* nnd, int* nn,
+                                    int* act, double* height, int* keep, PostScratch& sc, const Team& T) {
     const int tid = T.tid, NT = T.nthreads;
-    for (int i = tid; i < n; i += NT) { rep[i] = i; nodeid[i] = i; csize[i] = 1.0; flist[i] = i; }
-    if (tid == 0) sc.l_nflag = n;
+    for (int i = tid; i < n; i += NT) { rep[i] = i; csize[i] = 1.0; height[i] = -INFINITY; act[i] = i; }
     team_sync();
-    for (int step = 0; step < n - 2; ++step) {
-        // rescan the flagged rows, one warp per row
-        const int nflag = sc.l_nflag;
-        for (int f = T.warp; f < nflag; f += T.nwarps) {
-            const int a = flist[f];
+    int nact = n;
+    while (nact > 2) {
+        // 1. nearest neighbour of every active cluster, one warp per row.  act is ascending, so the
+        //    first minimum along a row is the tie-break by index.
+        for (int f = T.warp; f < nact; f += T.nwarps) {
+            const int a = act[f];
+            const double* row = D + (size_t)a * n;
             double bd = INFINITY;
             int bb = -1;
-            const double* row = D + (size_t)a * n;
-            // 8 independent loads per lane in flight (one memory round trip per 256 columns)
-            for (int b0 = a + 1 + T.lane; b0 < n; b0 += 8 * T.lanes) {
-                double v[8];
+            for (int g0 = T.lane; g0 < nact; g0 += 4 * T.lanes) {
+                double v[4];
+                int b[4];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) { const int b = b0 + u * T.lanes; v[u] = b < n ? row[b] : INFINITY; }
+                for (int u = 0; u < 4; ++u) {
+                    const int g = g0 + u * T.lanes;
+                    b[u] = g < nact ? act[g] : a;
+                    v[u] = b[u] != a ? row[b[u]] : INFINITY;
+                }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int b = b0 + u * T.lanes;
-                    if (b < n && nodeid[b] >= 0 && (bb < 0 || v[u] < bd)) { bd = v[u]; bb = b; }
+                for (int u = 0; u < 4; ++u) {
+                    if (b[u] == a) continue;
+                    const double x = isnan(v[u]) ? INFINITY : v[u];
+                    if (bb < 0 || x < bd) { bd = x; bb = b[u]; }
                 }
             }
             warp_min_pair(bd, bb);
-            if (T.lane == 0) { rmin[a] = bd; rarg[a] = bb; }
+            if (T.lane == 0) { nn[a] = bb; nnd[a] = bd; }
         }
         team_sync();
-        if (tid == 0) sc.l_nflag = 0;
-        double bd = INFINITY;
-        int ba = -1;
-        for (int a = tid; a < n; a += NT) {
-            if (nodeid[a] < 0 || rarg[a] < 0) continue;
-            double d = rmin[a];
-            if (ba < 0 || d < bd) { bd = d; ba = a; }
-        }
-        team_min_pair(bd, ba, sc, T);
-        const int a = sc.ia;
-        if (a < 0) break;
-        const int b = rarg[a];
-        const double na = csize[a], nb = csize[b];
-        team_sync();
-        // new distances of the merged cluster (kept at index a); its own row minimum on the fly
-        double ad = INFINITY;
-        int ac = -1;
-        for (int c = tid; c < n; c += NT) {
-            if (c == a || c == b || nodeid[c] < 0) continue;
-            double dn = (na * D[(size_t)a * n + c] + nb * D[(size_t)b * n + c]) / (na + nb);   // average_merge
-            D[(size_t)a * n + c] = dn;
-            D[(size_t)c * n + a] = dn;
-            if (c < a) {
-                if (rarg[c] == a || rarg[c] == b) {
-#if defined(__CUDACC__)
-                    flist[atomicAdd(&sc.l_nflag, 1)] = c;
-#else
-                    flist[sc.l_nflag++] = c;
-#endif
+        // 2. reciprocal pairs; the smaller index of a pair keeps the merged cluster (ordered list `keep`)
+        if (T.warp == 0) {
+            int k = 0;
+            for (int f0 = 0; f0 < nact; f0 += T.lanes) {
+                const int f = f0 + T.lane;
+                bool kp = false;
+                int a = -1;
+                if (f < nact) {
+                    a = act[f];
+                    const int b = nn[a];
+                    const bool rec = nn[b] == a;
+                    mate[a] = rec ? b : -1;
+                    kp = rec && a < b;
                 }
-                else if (dn < rmin[c] || (dn == rmin[c] && a < rarg[c])) { rmin[c] = dn; rarg[c] = a; }
-            } else {
-                if (c < b && rarg[c] == b) {
-#if defined(__CUDACC__)
-                    flist[atomicAdd(&sc.l_nflag, 1)] = c;
-#else
-                    flist[sc.l_nflag++] = c;
-#endif
-                }
-                if (ac < 0 || dn < ad) { ad = dn; ac = c; }
+                int tot;
+                const int pos = warp_rank(kp, tot);
+                if (kp) keep[k + pos] = a;
+                k += tot;
             }
+            if (T.lane == 0) sc.l_nflag = k;
         }
-        for (int i = tid; i < n; i += NT)
-            if (rep[i] == b) rep[i] = a;
-        team_min_pair(ad, ac, sc, T);
-        if (tid == 0) { csize[a] = na + nb; nodeid[a] = n + step; nodeid[b] = -1; rmin[a] = sc.da; rarg[a] = sc.ia; }
+        team_sync();
+        const int k = sc.l_nflag;
+        // 3. distances of the merged clusters to every surviving cluster.  Each new entry depends on
+        //    old entries that no other thread of this round writes.
+        for (int e = tid; e < k * nact; e += NT) {
+            const int X = keep[e / nact], Y = act[e % nact];
+            const int my = mate[Y];
+            if (Y == X || (my >= 0 && my < Y)) continue;         // itself / Y is absorbed this round
+            const bool ymerged = my > Y;
+            if (ymerged && Y < X) continue;                      // pair of merged clusters: done by (Y, X)
+            const int b = mate[X];
+            const double na = csize[X], nb = csize[b];
+            double v = (na * D[(size_t)X * n + Y] + nb * D[(size_t)b * n + Y]) / (na + nb);     // average_merge
+            if (ymerged) {
+                const double v2 = (na * D[(size_t)X * n + my] + nb * D[(size_t)b * n + my]) / (na + nb);
+                const double nc = csize[Y], nd = csize[my];
+                v = (nc * v + nd * v2) / (nc + nd);
+            }
+            D[(size_t)X * n + Y] = v;
+            D[(size_t)Y * n + X] = v;
+        }
+        team_sync();
+        // 4. bookkeeping, then drop the absorbed clusters from the active list (order kept)
+        for (int q = tid; q < k; q += NT) {
+            const int a = keep[q], b = mate[a];
+            height[a] = nnd[a];
+            csize[a] += csize[b];
+        }
+        for (int i = tid; i < n; i += NT) {
+            const int r = rep[i], m = mate[r];
+            if (m >= 0 && m < r) rep[i] = m;
+        }
+        if (T.warp == 0) {
+            int k2 = 0;
+            for (int f0 = 0; f0 < nact; f0 += T.lanes) {
+                const int f = f0 + T.lane;
+                bool kp = false;
+                int a = -1;
+                if (f < nact) { a = act[f]; const int m = mate[a]; kp = !(m >= 0 && m < a); }
+                int tot;
+                const int pos = warp_rank(kp, tot);
+                if (kp) act[k2 + pos] = a;                       // k2 + pos <= f: in place
+                k2 += tot;
+            }
+            if (T.lane == 0) sc.ia = k2;
+        }
+        team_sync();
+        nact = sc.ia;
         team_sync();
     }
-    // the two survivors; label 0 = larger node id
-    if (tid == 0) {
-        int c0 = -1, c1 = -1;
-        for (int i = 0; i < n; ++i)
-            if (nodeid[i] >= 0) { if (c0 < 0) c0 = i; else c1 = i; }
-        if (c1 >= 0 && nodeid[c1] > nodeid[c0]) { int t = c0; c0 = c1; c1 = t; }
-        sc.ia = c0; sc.ib = c1;
-    }
+    // the two survivors; label 0 = formed later
+    const int a0 = act[0], a1 = nact > 1 ? act[1] : act[0];
+    int c0 = a1;                                                 // equal heights (two leaves): the larger index
+    if (height[a0] > height[a1]) c0 = a0;
     team_sync();
-    const int c0 = sc.ia;
     for (int i = tid; i < n; i += NT) rep[i] = (rep[i] == c0) ? 0 : 1;
     team_sync();
 }
@@ -983,9 +1019,9 @@ VPK_DEVFN int split_best_vp(const Img& im, EmSlot& st, PostScratch& sc, double m
     const int worst = sc.ia;
     if (worst < 0) return -1;
     const int nw = st.cnt[worst];
-    // scratch layout (doubles): D[nw*nw] | csize[nw] | rmin[nw] | ints: idx rep nodeid rarg flist [nw each]
+    // scratch layout (doubles): D[nw*nw] | csize nnd height [nw each] | ints: idx rep mate nn act [nw each] keep [nw/2]
     // (the bookkeeping arrays live in shared memory when nw <= kLinkMax)
-    size_t need = (size_t)nw * nw + 2 * (size_t)nw + (5 * (size_t)nw + 1) / 2 + 4;
+    size_t need = (size_t)nw * nw + 3 * (size_t)nw + (11 * (size_t)nw / 2 + 3) / 2 + 4;
     double* scratch = im.lvsq;
     bool locked = false;
     // the line -> VP association and the line weights live outside the scratch region; the E/W
@@ -1002,14 +1038,17 @@ VPK_DEVFN int split_best_vp(const Img& im, EmSlot& st, PostScratch& sc, double m
     }
     double* D = scratch;
     double* csize = D + (size_t)nw * nw;
-    double* rmin = csize + nw;
-    int* idx = reinterpret_cast<int*>(rmin + nw);
+    double* nnd = csize + nw;
+    double* height = nnd + nw;
+    int* idx = reinterpret_cast<int*>(height + nw);
     int* rep = idx + nw;
-    int* nodeid = rep + nw;
-    int* rarg = nodeid + nw;
-    int* rflag = rarg + nw;
+    int* mate = rep + nw;
+    int* nn = mate + nw;
+    int* act = nn + nw;
+    int* keep = act + nw;
     if (nw <= kLinkMax) {
-        csize = sc.l_csize; rmin = sc.l_rmin; rep = sc.l_rep; nodeid = sc.l_nodeid; rarg = sc.l_rarg; rflag = sc.l_flist;
+        csize = sc.l_csize; nnd = sc.l_nnd; height = sc.l_height; rep = sc.l_rep; mate = sc.l_mate; nn = sc.l_nn;
+        act = sc.l_act; keep = sc.l_keep;
     }
     if (tid == 0) {
         int k = 0;
@@ -1023,7 +1062,7 @@ VPK_DEVFN int split_best_vp(const Img& im, EmSlot& st, PostScratch& sc, double m
         D[e] = d;
     }
     team_sync();
-    average_linkage_two(D, nw, rep, nodeid, csize, rmin, rarg, rflag, sc, T);
+    average_linkage_two(D, nw, rep, mate, csize, nnd, nn, act, height, keep, sc, T);
     // per cluster: smallest right-singular vector of the lweight-scaled lines (:580-602)
     for (int c = T.warp; c < 2; c += T.nwarps) {
         double g[6] = {0, 0, 0, 0, 0, 0};
