@@ -61,13 +61,25 @@ struct EmParams {
     const SlotDesc* desc;
     double* ws;
     int* lists;            // 2 x n_slots: active slot ids of the current / next superstep
-    int* ctl;              // [0],[1]: list lengths; [2]: overflow lock
+    int* ctl;              // [0],[1]: list lengths; [2]: overflow lock; [3]: supersteps done (parity = current list);
+                           // [4]: POST ticket counter; [5]: superstep limit hit
     unsigned long long* stats;   // nullable (profiling): [0] algorithmic bytes, [1] flops of the W products, [2] slot-products
     int n_slots;
     double* overflow;
     size_t overflow_cap;
     EmOut out;
 };
+
+// Loop control of the device-driven superstep loop (CUDA graph with conditional WHILE nodes, one per
+// tier of grid sizes): after every superstep the last POST block sets each tier's condition to
+// "more than thr[j] slots are still active".  n = 0: host-driven loop, nothing to set.
+constexpr int kMaxTiers = 8;
+struct TierCtl {
+    int n, max_steps;
+    int thr[kMaxTiers];
+    cudaGraphConditionalHandle h[kMaxTiers];
+};
+constexpr int kCtlInts = 8;
 
 // ---- PTX wrappers: mbarrier + 1-D bulk async copy (TMA engine, no tensor map) ----
 __device__ __forceinline__ uint32_t em_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -206,12 +218,12 @@ __global__ void __launch_bounds__(kInitThreads) em_init_kernel(EmParams P) {
 // warp order; the W operand tile is staged in shared memory and written with
 // contiguous stores.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kEThreads) em_estep_kernel(EmParams P, int cur) {
+__global__ void __launch_bounds__(kEThreads) em_estep_kernel(EmParams P) {
     constexpr int NW = kEThreads / 32, kMI = kMaxM / NW;
     __shared__ double c_pv[kMaxM], c_vx[kMaxM], c_vy[kMaxM], c_inv2s[kMaxM], c_coef[kMaxM];
     __shared__ double s_pl[NW][32];
     __shared__ double s_wt[kMaxM / kMP][32][kMP + 1];       // +1: conflict-free column writes
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) P.ctl[cur ^ 1] = 0;     // next superstep's list starts empty
+    const int cur = P.ctl[3] & 1;
     if ((int)blockIdx.y >= P.ctl[cur]) return;
     const int slot = P.lists[cur * P.n_slots + blockIdx.y];
     const EmSlot& st = P.slots[slot];
@@ -404,9 +416,10 @@ __device__ __forceinline__ void wmat_pass(WSmem& sm, const double* slab, const d
     }
 }
 
-__global__ void __launch_bounds__(kWThreads, 2) em_wmat_kernel(EmParams P, int cur, int csl) {
+__global__ void __launch_bounds__(kWThreads, 2) em_wmat_kernel(EmParams P, int csl) {
     extern __shared__ __align__(128) unsigned char w_smem_raw[];
     WSmem& sm = *reinterpret_cast<WSmem*>(w_smem_raw);
+    const int cur = P.ctl[3] & 1;
     if ((int)blockIdx.y >= P.ctl[cur]) return;
     const int slot = P.lists[cur * P.n_slots + blockIdx.y];
     const EmSlot& st = P.slots[slot];
@@ -476,29 +489,64 @@ __global__ void __launch_bounds__(kWThreads, 2) em_wmat_kernel(EmParams P, int c
 // ---------------------------------------------------------------------------
 // em_post: one CTA per active slot
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPostThreads) em_post_kernel(EmParams P, int cur) {
+__global__ void __launch_bounds__(kPostThreads) em_post_kernel(EmParams P, TierCtl tc) {
     __shared__ __align__(16) EmSlot st;
     __shared__ PostScratch sc;
-    if ((int)blockIdx.x >= P.ctl[cur]) return;
+    const int step = P.ctl[3], cur = step & 1;
     const Team T = make_team();
-    const int slot = P.lists[cur * P.n_slots + blockIdx.x];
-    copy_slot(&st, P.slots + slot, T);
+    if ((int)blockIdx.x < P.ctl[cur]) {
+        const int slot = P.lists[cur * P.n_slots + blockIdx.x];
+        copy_slot(&st, P.slots + slot, T);
+        __syncthreads();
+        const Img im = make_img(st.N, P.ws + st.ws_off, P.segs + 4 * (size_t)st.base);
+        post_slot(st, sc, im, P.out, P.cfg, P.overflow, P.overflow_cap, P.ctl + 2, T);
+        __syncthreads();
+        copy_slot(P.slots + slot, &st, T);
+        if (T.tid == 0 && !st.done) P.lists[(cur ^ 1) * P.n_slots + atomicAdd(P.ctl + (cur ^ 1), 1)] = slot;
+    }
+    // the last block to finish closes the superstep: the other list becomes current, this one is emptied
     __syncthreads();
-    const Img im = make_img(st.N, P.ws + st.ws_off, P.segs + 4 * (size_t)st.base);
-    post_slot(st, sc, im, P.out, P.cfg, P.overflow, P.overflow_cap, P.ctl + 2, T);
-    __syncthreads();
-    copy_slot(P.slots + slot, &st, T);
-    if (T.tid == 0 && !st.done) P.lists[(cur ^ 1) * P.n_slots + atomicAdd(P.ctl + (cur ^ 1), 1)] = slot;
+    if (T.tid == 0) {
+        __threadfence();
+        if (atomicAdd(P.ctl + 4, 1) == (int)gridDim.x - 1) {
+            __threadfence();
+            const int live = atomicAdd(P.ctl + (cur ^ 1), 0);
+            P.ctl[4] = 0;
+            P.ctl[cur] = 0;
+            P.ctl[3] = step + 1;
+            const bool stop = step + 1 >= tc.max_steps;
+            if (stop && live > 0) P.ctl[5] = 1;
+            for (int j = 0; j < tc.n; ++j) cudaGraphSetConditional(tc.h[j], (!stop && live > tc.thr[j]) ? 1u : 0u);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+// Device-driven loop: a CUDA graph of conditional WHILE nodes, one per tier of grid sizes
+// (n, n/4, n/16, ... slots); tier j repeats the superstep while more than bound[j+1] slots are
+// active (POST sets the conditions), so neither the host nor empty CTAs sit on the critical path.
+struct EmLoopGraph {
+    EmParams key;
+    int n = 0, nmax = 0;
+    int supersteps_per_iter = 0;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    void destroy() {
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        exec = nullptr; graph = nullptr;
+    }
+};
+
 struct EmState {
     DBuf ws, slots, desc, lists, ctl, stats, overflow, resp, out_small, out_assoc, out_dm, init_vp, init_off, sphere;
     HBuf h_desc, h_cnt;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool attr_set = false;
+    EmLoopGraph* loop = nullptr;
+    int last_supersteps = 0;
     unsigned long long totals[4] = {0, 0, 0, 0};   // accumulated W-product statistics + supersteps (profiling runs)
 };
 
@@ -509,19 +557,92 @@ void em_free(vpk_ctx* ctx) {
     e->resp.release(); e->out_small.release(); e->out_assoc.release(); e->out_dm.release(); e->init_vp.release();
     e->init_off.release(); e->sphere.release(); e->h_desc.release(); e->h_cnt.release();
     for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+    if (e->loop) { e->loop->destroy(); delete e->loop; }
     delete e;
     ctx->em = nullptr;
+}
+
+// one superstep on the stream (direct launch or stream capture): E -> W -> POST over `bound` slots
+static int enqueue_superstep(vpk_ctx* ctx, const EmParams& P, int bound, int nmax, int csl, const TierCtl& tc, bool scoped) {
+    cudaStream_t sm = ctx->stream;
+    const int tiles = (nmax + kTK - 1) / kTK;
+    {
+        KernelScope ks(ctx, "em_estep", scoped);
+        em_estep_kernel<<<dim3((nmax + 31) / 32, bound), kEThreads, 0, sm>>>(P);
+        VPK_TRY(check_launch("em_estep"));
+    }
+    {
+        KernelScope ks(ctx, "em_wmat", scoped);
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(tiles * csl, bound);
+        lc.blockDim = dim3(kWThreads);
+        lc.dynamicSmemBytes = sizeof(WSmem);
+        lc.stream = sm;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = csl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        VPK_CUDA(cudaLaunchKernelEx(&lc, em_wmat_kernel, P, csl));
+        VPK_TRY(check_launch("em_wmat"));
+    }
+    {
+        KernelScope ks(ctx, "em_post", scoped);
+        em_post_kernel<<<bound, kPostThreads, 0, sm>>>(P, tc);
+        VPK_TRY(check_launch("em_post"));
+    }
+    return VPK_OK;
+}
+
+static int build_loop_graph(vpk_ctx* ctx, EmLoopGraph& G, const EmParams& P, int n, int nmax, int max_steps) {
+    G.destroy();
+    const int csl = wmat_split(nmax);
+    VPK_CUDA(cudaGraphCreate(&G.graph, 0));
+    TierCtl tc;
+    memset(&tc, 0, sizeof(tc));
+    tc.max_steps = max_steps;
+    int bound[kMaxTiers + 1];
+    int nt = 0;
+    bound[0] = n;
+    while (nt + 1 < kMaxTiers && bound[nt] > 8) { bound[nt + 1] = (bound[nt] + 3) / 4; ++nt; }
+    ++nt;                                         // tiers 0 .. nt-1
+    tc.n = nt;
+    for (int j = 0; j < nt; ++j) {
+        tc.thr[j] = j + 1 < nt ? bound[j + 1] : 0;
+        VPK_CUDA(cudaGraphConditionalHandleCreate(&tc.h[j], G.graph, 1, cudaGraphCondAssignDefault));
+    }
+    cudaGraphNode_t prev = nullptr;
+    for (int j = 0; j < nt; ++j) {
+        cudaGraphNodeParams np = {};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = tc.h[j];
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t node;
+        VPK_CUDA(cudaGraphAddNode(&node, G.graph, prev ? &prev : nullptr, prev ? 1 : 0, &np));
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        VPK_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+        int rc = enqueue_superstep(ctx, P, bound[j], nmax, csl, tc, false);
+        cudaGraph_t dummy = nullptr;
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &dummy);
+        if (rc != VPK_OK) return rc;
+        VPK_CUDA(e);
+        prev = node;
+    }
+    VPK_CUDA(cudaGraphInstantiate(&G.exec, G.graph, 0));
+    G.key = P; G.n = n; G.nmax = nmax;
+    return VPK_OK;
 }
 
 // one wave: slots [0, n) described by h_desc (already in pinned memory)
 static int em_wave(vpk_ctx* ctx, EmState* st, EmParams& P, int n, int nmax) {
     cudaStream_t sm = ctx->stream;
     VPK_CUDA(cudaMemcpyAsync(st->desc.p, st->h_desc.p, sizeof(SlotDesc) * (size_t)n, cudaMemcpyHostToDevice, sm));
-    VPK_CUDA(cudaMemsetAsync(st->ctl.p, 0, 4 * sizeof(int), sm));
+    VPK_CUDA(cudaMemsetAsync(st->ctl.p, 0, kCtlInts * sizeof(int), sm));
     if (P.stats) VPK_CUDA(cudaMemsetAsync(P.stats, 0, 4 * sizeof(unsigned long long), sm));
     P.n_slots = n;
     const int tiles = (nmax + kTK - 1) / kTK;
     const int csl = wmat_split(nmax);         // cluster size of the W launches (slots use min(wmat_split(N), csl))
+    const int max_steps = 64 * (P.cfg.num_iter + 8);
     if (P.cfg.use_weights) {
         KernelScope ks(ctx, "em_pair");
         em_pair_kernel<<<dim3(tiles, n), kPairThreads, 0, sm>>>(P);
@@ -533,48 +654,41 @@ static int em_wave(vpk_ctx* ctx, EmState* st, EmParams& P, int n, int nmax) {
         VPK_TRY(check_launch("em_init"));
     }
     int* h_cnt = st->h_cnt.as<int>();
+    static const bool host_loop = getenv("VPK_EM_HOST_LOOP") != nullptr;
+    if (!ctx->profiling && !host_loop) {
+        // ---- device-driven loop (no per-kernel events possible inside a graph: profiling runs use the host loop)
+        EmLoopGraph& G = *st->loop;
+        if (!G.exec || G.n != n || G.nmax != nmax || memcmp(&G.key, &P, sizeof(EmParams)) != 0)
+            VPK_TRY(build_loop_graph(ctx, G, P, n, nmax, max_steps));
+        VPK_CUDA(cudaGraphLaunch(G.exec, sm));
+        VPK_CUDA(cudaMemcpyAsync(h_cnt, P.ctl, kCtlInts * sizeof(int), cudaMemcpyDeviceToHost, sm));
+        VPK_CUDA(cudaStreamSynchronize(sm));
+        ctx->launches += 3 * (int64_t)h_cnt[3];
+        st->last_supersteps = h_cnt[3];
+        if (h_cnt[5]) { set_error("vpk_em: supersteps did not terminate"); return VPK_ERR_STATE; }
+        return VPK_OK;
+    }
+    // ---- host-driven loop: supersteps enqueued in chunks, the active count read LA chunks behind
+    TierCtl tc;
+    memset(&tc, 0, sizeof(tc));
+    tc.max_steps = max_steps;
     int bound = n;              // upper bound of the number of active slots (they only ever finish)
     int step = 0;
     static const int LA = getenv("VPK_EM_LOOKAHEAD") ? atoi(getenv("VPK_EM_LOOKAHEAD")) : 3;
     for (int chunk = 0;; ++chunk) {
         if (chunk >= LA) {
             VPK_CUDA(cudaEventSynchronize(st->ev[(chunk - LA) & 7]));
-            bound = h_cnt[(chunk - LA) & 7];
+            bound = h_cnt[8 + ((chunk - LA) & 7)];
             if (bound <= 0) break;
         }
-        for (int k = 0; k < kChunkSteps; ++k, ++step) {
-            const int cur = step & 1;
-            {
-                KernelScope ks(ctx, "em_estep");
-                em_estep_kernel<<<dim3((nmax + 31) / 32, bound), kEThreads, 0, sm>>>(P, cur);
-                VPK_TRY(check_launch("em_estep"));
-            }
-            {
-                KernelScope ks(ctx, "em_wmat");
-                cudaLaunchConfig_t lc = {};
-                lc.gridDim = dim3(tiles * csl, bound);
-                lc.blockDim = dim3(kWThreads);
-                lc.dynamicSmemBytes = sizeof(WSmem);
-                lc.stream = sm;
-                cudaLaunchAttribute at[1];
-                at[0].id = cudaLaunchAttributeClusterDimension;
-                at[0].val.clusterDim.x = csl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-                lc.attrs = at; lc.numAttrs = 1;
-                VPK_CUDA(cudaLaunchKernelEx(&lc, em_wmat_kernel, P, cur, csl));
-                VPK_TRY(check_launch("em_wmat"));
-            }
-            {
-                KernelScope ks(ctx, "em_post");
-                em_post_kernel<<<bound, kPostThreads, 0, sm>>>(P, cur);
-                VPK_TRY(check_launch("em_post"));
-            }
-        }
+        for (int k = 0; k < kChunkSteps; ++k, ++step) VPK_TRY(enqueue_superstep(ctx, P, bound, nmax, csl, tc, true));
         // length of the list the next superstep will read
-        VPK_CUDA(cudaMemcpyAsync(h_cnt + (chunk & 7), P.ctl + (step & 1), sizeof(int), cudaMemcpyDeviceToHost, sm));
+        VPK_CUDA(cudaMemcpyAsync(h_cnt + 8 + (chunk & 7), P.ctl + (step & 1), sizeof(int), cudaMemcpyDeviceToHost, sm));
         VPK_CUDA(cudaEventRecord(st->ev[chunk & 7], sm));
-        if (step > 64 * (P.cfg.num_iter + 8)) { set_error("vpk_em: supersteps did not terminate"); return VPK_ERR_STATE; }
+        if (step > max_steps) { set_error("vpk_em: supersteps did not terminate"); return VPK_ERR_STATE; }
     }
     VPK_CUDA(cudaStreamSynchronize(sm));
+    st->last_supersteps = step;
     if (P.stats) {
         unsigned long long h[4] = {0, 0, 0, 0};
         VPK_CUDA(cudaMemcpy(h, P.stats, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -606,11 +720,13 @@ int em_dev(vpk_ctx* ctx, const double* d_lines, const double* d_segments, const 
     size_t free_b = 0, total_b = 0;
     VPK_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const size_t budget = std::max<size_t>((free_b + st->ws.cap) / 2, (size_t)1 << 28) / sizeof(double);
-    VPK_TRY(st->h_cnt.ensure(8 * sizeof(int)));
-    VPK_TRY(st->ctl.ensure(4 * sizeof(int)));
+    VPK_TRY(st->h_cnt.ensure(16 * sizeof(int)));
+    if (!st->loop) st->loop = new EmLoopGraph();
+    VPK_TRY(st->ctl.ensure(kCtlInts * sizeof(int)));
     VPK_TRY(st->stats.ensure(4 * sizeof(unsigned long long)));
 
     EmParams P;
+    memset(&P, 0, sizeof(P));                   // padding included: the loop graph is keyed on the bytes
     P.lines = d_lines; P.segs = d_segments;
     P.resp32 = d_resp_f32; P.resp64 = d_resp_f64; P.sphere = d_sphere; P.S = S;
     P.init_vp = d_init_vp; P.init_off = d_init_off;

@@ -116,15 +116,17 @@ struct KernelScope {
     vpk_ctx* ctx;
     const char* name;
     cudaEvent_t a = nullptr, b = nullptr;
-    KernelScope(vpk_ctx* c, const char* n) : ctx(c), name(n) {
-        ctx->launches++;
-        if (ctx->profiling) {
+    bool timed;
+    // counted = false: the launch is being captured into a graph (counted when the graph runs, no events)
+    KernelScope(vpk_ctx* c, const char* n, bool counted = true) : ctx(c), name(n), timed(counted && c->profiling) {
+        if (counted) ctx->launches++;
+        if (timed) {
             a = take(); b = take();
             cudaEventRecord(a, ctx->stream);
         }
     }
     ~KernelScope() {
-        if (ctx->profiling) {
+        if (timed) {
             cudaEventRecord(b, ctx->stream);
             ctx->pending.push_back({name, a, b});
         }
