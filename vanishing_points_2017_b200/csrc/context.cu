@@ -61,6 +61,7 @@ int vpk_create(int device, vpk_ctx** out) {
     vpk_ctx* ctx = new vpk_ctx();
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
+    ctx->l2_bytes = (size_t)prop.l2CacheSize;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_error("cudaStreamCreate -> %s", cudaGetErrorString(e)); delete ctx; return VPK_ERR_CUDA; }
     *out = ctx;

@@ -39,7 +39,8 @@ static constexpr int kPairThreads = 256;
 static constexpr int kEThreads = 256;
 static constexpr int kWThreads = 256;
 static constexpr int kJR = 32;             // lsim rows per pipeline stage of the W kernel
-static constexpr int kStages = 4;
+static constexpr int kStages = 4;            // ring depth of the W kernel when the GPU is full (2 CTAs / SM)
+static constexpr int kStagesTail = 8;        // ... when fewer CTAs than SMs are left: per-CTA streaming is latency bound
 static constexpr int kChunkSteps = 4;      // supersteps enqueued between two host polls
 
 struct SlotDesc {
@@ -298,10 +299,11 @@ __global__ void __launch_bounds__(kEThreads) em_estep_kernel(EmParams P) {
 // order through distributed shared memory.  CS depends on N only, so an image's
 // result does not depend on what else is in the batch.
 // ---------------------------------------------------------------------------
-struct WSmem {
-    double a[kStages][kJR * kTK];          // lsim rows
-    double b[kStages][kJR * kMP];          // wt rows; reused for the per-CTA partial result (kMP x kTK)
-    unsigned long long full[kStages], empty[kStages];
+template <int STAGES>
+struct WSmemT {
+    double a[STAGES][kJR * kTK];           // lsim rows
+    double b[STAGES][kJR * kMP];           // wt rows; reused for the per-CTA partial result (kMP x kTK)
+    unsigned long long full[STAGES], empty[STAGES];
 };
 
 // CTAs per slab: only very tall slabs are split (the cluster barriers cost ~20 % of a short CTA's time)
@@ -332,9 +334,9 @@ __device__ __forceinline__ double em_ld_dsmem(const double* local, uint32_t rank
 }
 
 // main loop of one pass for R VP rows per thread: chunks [c0, c1) of the slab
-template <int R>
-__device__ __forceinline__ void wmat_pass(WSmem& sm, const double* slab, const double* wtp, int ws, int N, int c0, int c1,
-                                          int G, int& ring, uint64_t policy, double* red, double* part) {
+template <int R, int kStages>
+__device__ __forceinline__ void wmat_pass(WSmemT<kStages>& sm, const double* slab, const double* wtp, int ws, int N, int c0, int c1,
+                                          int G, int& ring, uint64_t policy, bool keep, double* red, double* part) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int NWARP = kWThreads / 32;
     const int wpg = NWARP / G;                       // warps per group
@@ -349,7 +351,8 @@ __device__ __forceinline__ void wmat_pass(WSmem& sm, const double* slab, const d
         const int j0 = (c0 + i) * kJR, jn = min(kJR, N - j0), s = (ring + i) % kStages;
         const uint32_t bar = em_smem_u32(&sm.full[s]);
         em_mbar_expect_tx(bar, (uint32_t)(jn * (kTK + ws) * sizeof(double)));
-        em_bulk_g2s_hint(em_smem_u32(sm.a[s]), slab + (size_t)j0 * kTK, (uint32_t)(jn * kTK * sizeof(double)), bar, policy);
+        if (keep) em_bulk_g2s(em_smem_u32(sm.a[s]), slab + (size_t)j0 * kTK, (uint32_t)(jn * kTK * sizeof(double)), bar);
+        else em_bulk_g2s_hint(em_smem_u32(sm.a[s]), slab + (size_t)j0 * kTK, (uint32_t)(jn * kTK * sizeof(double)), bar, policy);
         em_bulk_g2s(em_smem_u32(sm.b[s]), wtp + (size_t)j0 * ws, (uint32_t)(jn * ws * sizeof(double)), bar);
     };
     for (int i = 0; i < nch; ++i) {
@@ -416,9 +419,12 @@ __device__ __forceinline__ void wmat_pass(WSmem& sm, const double* slab, const d
     }
 }
 
-__global__ void __launch_bounds__(kWThreads, 2) em_wmat_kernel(EmParams P, int csl) {
+// keep: the similarity matrices of the slots still active fit the L2, so they are loaded with the
+// default policy and stay resident from one superstep to the next (evict-first otherwise).
+template <int kStages>
+__global__ void __launch_bounds__(kWThreads, 2) em_wmat_kernel(EmParams P, int csl, int keep) {
     extern __shared__ __align__(128) unsigned char w_smem_raw[];
-    WSmem& sm = *reinterpret_cast<WSmem*>(w_smem_raw);
+    WSmemT<kStages>& sm = *reinterpret_cast<WSmemT<kStages>*>(w_smem_raw);
     const int cur = P.ctl[3] & 1;
     if ((int)blockIdx.y >= P.ctl[cur]) return;
     const int slot = P.lists[cur * P.n_slots + blockIdx.y];
@@ -463,10 +469,10 @@ __global__ void __launch_bounds__(kWThreads, 2) em_wmat_kernel(EmParams P, int c
         const int ws = G * R;
         const double* wtp = im.wt + (size_t)pass * N * kMP;
         switch (R) {
-        case 4: wmat_pass<4>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, red, part); break;
-        case 8: wmat_pass<8>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, red, part); break;
-        case 12: wmat_pass<12>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, red, part); break;
-        default: wmat_pass<16>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, red, part); break;
+        case 4: wmat_pass<4, kStages>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, keep != 0, red, part); break;
+        case 8: wmat_pass<8, kStages>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, keep != 0, red, part); break;
+        case 12: wmat_pass<12, kStages>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, keep != 0, red, part); break;
+        default: wmat_pass<16, kStages>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, keep != 0, red, part); break;
         }
         if (csl > 1) em_cluster_sync(); else __syncthreads();          // partial results are complete
         if (rank == 0) {
@@ -576,13 +582,17 @@ static int enqueue_superstep(vpk_ctx* ctx, const EmParams& P, int bound, int nma
         cudaLaunchConfig_t lc = {};
         lc.gridDim = dim3(tiles * csl, bound);
         lc.blockDim = dim3(kWThreads);
-        lc.dynamicSmemBytes = sizeof(WSmem);
+        // fewer CTAs than SMs: deeper ring; similarity matrices of the active slots within half the L2: keep them there
+        const bool tail = (long long)tiles * csl * bound <= (long long)ctx->num_sms;
+        const int keep = 8.0 * nmax * nmax * bound <= 0.5 * (double)ctx->l2_bytes ? 1 : 0;
+        lc.dynamicSmemBytes = tail ? sizeof(WSmemT<kStagesTail>) : sizeof(WSmemT<kStages>);
         lc.stream = sm;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = csl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         lc.attrs = at; lc.numAttrs = 1;
-        VPK_CUDA(cudaLaunchKernelEx(&lc, em_wmat_kernel, P, csl));
+        if (tail) VPK_CUDA(cudaLaunchKernelEx(&lc, em_wmat_kernel<kStagesTail>, P, csl, keep));
+        else VPK_CUDA(cudaLaunchKernelEx(&lc, em_wmat_kernel<kStages>, P, csl, keep));
         VPK_TRY(check_launch("em_wmat"));
     }
     {
@@ -707,7 +717,8 @@ int em_dev(vpk_ctx* ctx, const double* d_lines, const double* d_segments, const 
     if (!ctx->em) ctx->em = new EmState();
     EmState* st = ctx->em;
     if (!st->attr_set) {
-        VPK_CUDA(cudaFuncSetAttribute(em_wmat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WSmem)));
+        VPK_CUDA(cudaFuncSetAttribute(em_wmat_kernel<kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WSmemT<kStages>)));
+        VPK_CUDA(cudaFuncSetAttribute(em_wmat_kernel<kStagesTail>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WSmemT<kStagesTail>)));
         for (auto& ev : st->ev) VPK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         st->attr_set = true;
     }

@@ -359,16 +359,18 @@ VPK_DEVFN bool smallest_eigvec3(const double g[6], double out[3]) {
             if (isnan(a[i][j])) return false;
     for (int sweep = 0; sweep < 24; ++sweep) {
         double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
-        if (off < 1e-40) break;
+        if (off < 1e-36) break;                 // off-diagonal below 1e-18 of the trace: converged in float64
 #pragma unroll
         for (int pq = 0; pq < 3; ++pq) {
             const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
             double apq = a[p][q];
             if (apq == 0.0) continue;
-            double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
-            double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-            if (isinf(theta)) t = 0.0;
-            double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+            // tan of the rotation angle, t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)) with
+            // theta = (aqq - app) / (2 apq), written with one square root and one division
+            const double d = a[q][q] - a[p][p], b2 = 2.0 * apq;
+            const double den = fabs(d) + sqrt(d * d + b2 * b2);
+            const double t = den > 0.0 ? (d >= 0 ? b2 : -b2) / den : 1.0;      // den == 0: underflow, theta = 0
+            const double c = rsqrt(t * t + 1.0), sn = t * c;
             double app = a[p][p], aqq = a[q][q];
             a[p][p] = app - t * apq;
             a[q][q] = aqq + t * apq;
@@ -385,10 +387,14 @@ VPK_DEVFN bool smallest_eigvec3(const double g[6], double out[3]) {
             }
         }
     }
+    // column of the smallest diagonal entry (first one on ties); selects instead of dynamic indexing
     int m = 0;
-    if (a[1][1] < a[m][m]) m = 1;
-    if (a[2][2] < a[m][m]) m = 2;
-    double x = v[0][m], y = v[1][m], z = v[2][m];
+    double dm = a[0][0];
+    if (a[1][1] < dm) { m = 1; dm = a[1][1]; }
+    if (a[2][2] < dm) m = 2;
+    const double x = m == 0 ? v[0][0] : (m == 1 ? v[0][1] : v[0][2]);
+    const double y = m == 0 ? v[1][0] : (m == 1 ? v[1][1] : v[1][2]);
+    const double z = m == 0 ? v[2][0] : (m == 1 ? v[2][1] : v[2][2]);
     double n = sqrt(x * x + y * y + z * z);
     if (!(n > 0.0)) return false;
     out[0] = x / n; out[1] = y / n; out[2] = z / n;
@@ -723,15 +729,22 @@ VPK_DEVFN void line_counts(const Img& im, EmSlot& st, double thresh, const Team&
     team_sync();
 }
 
-// E7 + E8 for one VP by one warp.
+// E7 + E8 in two parts, so that the dependent scalar chains of all VPs (3x3 eigen-solve, log/exp)
+// run side by side instead of once per warp round:
+//   refit_sums  : one warp sweeps the lines twice (row maximum, then every sum at once) -> RefitAcc
+//   refit_finish: one thread per VP solves, another one evaluates sigma
 // E7: smallest eigenvector of sum (w/max w)^2 l l^T over the selected lines (sel < 0: all lines;
 // sel >= 0: only lines with assoc == sel, the final refit).  wrow2: optional second weight row
-// added to the first (merge).  Returns false where calc_new_vanishing_point returns None.
-// E8: *s_out = exp(log(sum lvsq*pvl) - log(sum pvl)) over ALL lines for VP row vm
+// added to the first (merge).  ok = 0 where calc_new_vanishing_point returns None.
+// E8: sv = exp(log(sum lvsq*pvl) - log(sum pvl)) over ALL lines for VP row vm
 // (vp_localisation.py:301-304), or the pooled form of merge_vps (:663-664) if vm2 >= 0.
-// Two sweeps over the lines: the row maximum, then every sum at once.
-VPK_DEVFN bool refit_vp(const Img& im, const double* wrow, const double* wrow2, int sel, int vm, int vm2, double out[3],
-                        double* s_out, const Team& T) {
+struct RefitAcc {
+    double g[6], num, den, a1[3];      // a1: the only selected row, scaled (rows == 1)
+    double nv[3], sv;                  // results
+    int rows, fit, any, ok;
+};
+VPK_DEVFN void refit_sums(const Img& im, const double* wrow, const double* wrow2, int sel, int vm, int vm2, RefitAcc& acc,
+                          const Team& T) {
     const int N = im.N;
     double mx = -INFINITY;
     bool any = false;
@@ -769,20 +782,30 @@ VPK_DEVFN bool refit_vp(const Img& im, const double* wrow, const double* wrow2, 
     }
     num = warp_sum(num);
     den = warp_sum(den);
-    *s_out = exp(log(num) - log(den));
-    if (!fit) return false;
 #pragma unroll
     for (int k = 0; k < 6; ++k) g[k] = warp_sum(g[k]);
     rows = warp_sum_i(rows);
     only = warp_max_i(only);
+    if (T.lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc.g[k] = g[k];
+        acc.num = num; acc.den = den; acc.rows = rows; acc.fit = fit ? 1 : 0; acc.any = any ? 1 : 0;
+        if (fit && rows == 1) {
+            const double x = (wrow[only] + (wrow2 ? wrow2[only] : 0.0)) / mx;
+            acc.a1[0] = x * im.ln[3 * (size_t)only]; acc.a1[1] = x * im.ln[3 * (size_t)only + 1]; acc.a1[2] = x * im.ln[3 * (size_t)only + 2];
+        }
+    }
+}
+VPK_DEVFN void refit_solve(RefitAcc& acc) {
+    acc.ok = 0;
+    if (!acc.fit) return;
     double e[3];
     bool okv;
-    if (rows == 1) {
+    if (acc.rows == 1) {
         // A single 1x3 row has a 2-D null space; LAPACK's full SVD (what numpy.linalg.svd runs,
         // vp_localisation.py:466) completes V with the Householder reflector of dgelqf/dlarfg:
         // V[:,2] = row 3 of H = I - tau v v^T, v = (1, a2/(a1-beta), a3/(a1-beta)).
-        double x = (wrow[only] + (wrow2 ? wrow2[only] : 0.0)) / mx;
-        double a1 = x * im.ln[3 * (size_t)only], a2 = x * im.ln[3 * (size_t)only + 1], a3 = x * im.ln[3 * (size_t)only + 2];
+        const double a1 = acc.a1[0], a2 = acc.a1[1], a3 = acc.a1[2];
         double nrm = sqrt(a1 * a1 + a2 * a2 + a3 * a3);
         double beta = -copysign(nrm, a1);
         double tau = (beta - a1) / beta;
@@ -792,13 +815,28 @@ VPK_DEVFN bool refit_vp(const Img& im, const double* wrow, const double* wrow2, 
         okv = n2 > 0.0 && !isnan(n2);
         if (okv) { e[0] /= n2; e[1] /= n2; e[2] /= n2; }
     } else {
-        okv = smallest_eigvec3(g, e);
+        okv = smallest_eigvec3(acc.g, e);
     }
-    if (!okv) return false;
+    if (!okv) return;
     double sg = sign_np(e[2]);                                           // :474
-    out[0] = e[0] * sg; out[1] = e[1] * sg; out[2] = e[2] * sg;
-    return true;
+    acc.nv[0] = e[0] * sg; acc.nv[1] = e[1] * sg; acc.nv[2] = e[2] * sg;
+    acc.ok = 1;
 }
+// the scalar tails of `count` refits: thread q < kMaxM solves VP q, thread kMaxM + q evaluates its sigma
+VPK_DEVFN void refit_finish(RefitAcc* acc, int count, const Team& T) {
+    team_sync();
+    for (int q = T.tid; q < 2 * kMaxM; q += T.nthreads) {
+        const int m = q % kMaxM;
+        if (m >= count) continue;
+        if (q < kMaxM) refit_solve(acc[m]);
+        else acc[m].sv = exp(log(acc[m].num) - log(acc[m].den));
+    }
+    team_sync();
+}
+
+// the accumulators live on the (idle) average-linkage bookkeeping of the POST scratch
+static_assert(sizeof(RefitAcc) * kMaxM <= 3 * kLinkMax * sizeof(double), "RefitAcc overlay");
+VPK_DEV RefitAcc* refit_acc(PostScratch& sc) { return reinterpret_cast<RefitAcc*>(sc.l_nnd); }
 
 // remove the VPs flagged in rem[] from cur / nxt / s (numpy.delete along the VP axis)
 VPK_DEVFN void compact_vps(EmSlot& st, const int* rem, const Team& T) {
@@ -1221,36 +1259,39 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
             return;
         }
         case PH_MSTEP: {
-            // ---- M-step (:284-322), one warp per VP
+            // ---- M-step (:284-322): sums by one warp per VP, then the scalar tails side by side
             const int M = st.M;
-            for (int m = T.warp; m < M; m += T.nwarps) {
+            RefitAcc* acc = refit_acc(sc);
+            if (cfg.do_iterations) {
+                for (int m = T.warp; m < M; m += T.nwarps) refit_sums(im, im.w + (size_t)m * N, nullptr, -1, m, -1, acc[m], T);
+                refit_finish(acc, M, T);
+            }
+            for (int m = T.tid; m < M; m += T.nthreads) {
                 if (!cfg.do_iterations) {
-                    if (T.lane == 0) { sc.rem[m] = 0; sc.err[m] = 0.0; for (int c = 0; c < 3; ++c) st.nxt[m][c] = st.cur[m][c]; }
+                    sc.rem[m] = 0; sc.err[m] = 0.0;
+                    for (int c = 0; c < 3; ++c) st.nxt[m][c] = st.cur[m][c];
                     continue;
                 }
-                double nv[3];
-                double sv = 0.0;
-                bool okv = refit_vp(im, im.w + (size_t)m * N, nullptr, -1, m, -1, nv, &sv, T);
-                if (T.lane == 0) {
-                    int rem = 0;
-                    double err = 0.0;
-                    if (!okv) rem = 1;
+                int rem = 0;
+                double err = 0.0;
+                if (!acc[m].ok) rem = 1;
+                else {
+                    const double* nv = acc[m].nv;
+                    double sv = acc[m].sv;
+                    st.nxt[m][0] = nv[0]; st.nxt[m][1] = nv[1]; st.nxt[m][2] = nv[2];
+                    sv = isnan(sv) ? sv : fmin(sv, max_stdd);                  // :306
+                    sv = isnan(sv) ? sv : fmax(sv, cfg.s_thresh);              // :307
+                    st.s[m] = sv;
+                    if (isnan(sv)) rem = 1;
                     else {
-                        st.nxt[m][0] = nv[0]; st.nxt[m][1] = nv[1]; st.nxt[m][2] = nv[2];
-                        sv = isnan(sv) ? sv : fmin(sv, max_stdd);                  // :306
-                        sv = isnan(sv) ? sv : fmax(sv, cfg.s_thresh);              // :307
-                        st.s[m] = sv;
-                        if (isnan(sv)) rem = 1;
-                        else {
-                            double d = fabs(st.cur[m][0] * nv[0] + st.cur[m][1] * nv[1] + st.cur[m][2] * nv[2]);
-                            err = acos(fmin(d, 1.0));                               // :312
-                            if (isnan(d)) err = d;
-                            if (err > 1.5) rem = 1;
-                        }
+                        double d = fabs(st.cur[m][0] * nv[0] + st.cur[m][1] * nv[1] + st.cur[m][2] * nv[2]);
+                        err = acos(fmin(d, 1.0));                               // :312
+                        if (isnan(d)) err = d;
+                        if (err > 1.5) rem = 1;
                     }
-                    sc.rem[m] = rem;
-                    sc.err[m] = err;
                 }
+                sc.rem[m] = rem;
+                sc.err[m] = err;
             }
             team_sync();
             if (T.tid == 0) {
@@ -1326,15 +1367,14 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
         }
         case PH_MERGE_EVAL: {
             const int j = st.merge_j, k = st.merge_k, M = st.M;
-            if (T.warp == 0) {
-                double nv[3];
-                double sk = 0.0;
-                bool okv = refit_vp(im, im.w + (size_t)j * N, im.w + (size_t)k * N, -1, k, j, nv, &sk, T);
-                if (T.lane == 0) {
-                    st.s[k] = sk;                                  // assigned before the test (:666)
-                    sc.flag = (okv && !(sk > 0.01)) ? 1 : 0;       // max_stdd = 0.01 (:633, :668)
-                    if (sc.flag) { st.nxt[k][0] = nv[0]; st.nxt[k][1] = nv[1]; st.nxt[k][2] = nv[2]; }
-                }
+            RefitAcc* acc = refit_acc(sc);
+            if (T.warp == 0) refit_sums(im, im.w + (size_t)j * N, im.w + (size_t)k * N, -1, k, j, acc[0], T);
+            refit_finish(acc, 1, T);
+            if (T.tid == 0) {
+                const double sk = acc[0].sv;
+                st.s[k] = sk;                                  // assigned before the test (:666)
+                sc.flag = (acc[0].ok && !(sk > 0.01)) ? 1 : 0;       // max_stdd = 0.01 (:633, :668)
+                if (sc.flag) { st.nxt[k][0] = acc[0].nv[0]; st.nxt[k][1] = acc[0].nv[1]; st.nxt[k][2] = acc[0].nv[2]; }
             }
             team_sync();
             if (!sc.flag) { ph = st.after_merge; break; }
@@ -1360,30 +1400,27 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
             argmax_assoc(im, st.M, T);
             // hard-assignment refit (:353-392)
             const int M2 = st.M;
-            for (int m = T.warp; m < M2; m += T.nwarps) {
-                bool have = false;
-                for (int n = T.lane; n < N; n += T.lanes) have = have || (im.assoc[n] == m);
-                have = warp_any(have);
-                if (!have) { if (T.lane == 0) sc.rem[m] = 0; continue; }
-                double nv[3];
-                double sv = 0.0;
-                bool okv = refit_vp(im, im.w + (size_t)m * N, nullptr, m, m, -1, nv, &sv, T);
-                if (T.lane == 0) {
-                    int rem = 0;
-                    if (!okv) rem = 1;
+            RefitAcc* acc = refit_acc(sc);
+            for (int m = T.warp; m < M2; m += T.nwarps) refit_sums(im, im.w + (size_t)m * N, nullptr, m, m, -1, acc[m], T);
+            refit_finish(acc, M2, T);
+            for (int m = T.tid; m < M2; m += T.nthreads) {
+                if (!acc[m].any) { sc.rem[m] = 0; continue; }              // no line assigned: left as it is (:354-356)
+                int rem = 0;
+                if (!acc[m].ok) rem = 1;
+                else {
+                    const double* nv = acc[m].nv;
+                    double sv = acc[m].sv;
+                    st.nxt[m][0] = nv[0]; st.nxt[m][1] = nv[1]; st.nxt[m][2] = nv[2];
+                    sv = isnan(sv) ? sv : fmin(sv, max_stdd);               // :377
+                    st.s[m] = sv;
+                    if (isnan(sv) || sv < cfg.s_thresh) rem = 1;            // :379
                     else {
-                        st.nxt[m][0] = nv[0]; st.nxt[m][1] = nv[1]; st.nxt[m][2] = nv[2];
-                        sv = isnan(sv) ? sv : fmin(sv, max_stdd);               // :377
-                        st.s[m] = sv;
-                        if (isnan(sv) || sv < cfg.s_thresh) rem = 1;            // :379
-                        else {
-                            double d = fabs(st.cur[m][0] * nv[0] + st.cur[m][1] * nv[1] + st.cur[m][2] * nv[2]);
-                            double err = acos(fmin(d, 1.0));
-                            if (err > 1.5) rem = 1;
-                        }
+                        double d = fabs(st.cur[m][0] * nv[0] + st.cur[m][1] * nv[1] + st.cur[m][2] * nv[2]);
+                        double err = acos(fmin(d, 1.0));
+                        if (err > 1.5) rem = 1;
                     }
-                    sc.rem[m] = rem;
                 }
+                sc.rem[m] = rem;
             }
             compact_vps(st, sc.rem, T);
             if (st.M == 0) {                                    // "decision metric is empty" (:400-404)

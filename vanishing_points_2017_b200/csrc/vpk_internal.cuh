@@ -92,6 +92,7 @@ struct PipeState;  // pipeline.cu
 struct vpk_ctx {
     int device = 0;
     int num_sms = 148;
+    size_t l2_bytes = 126u << 20;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
     bool profiling = false;
