@@ -151,8 +151,10 @@ VPK_API int vpk_em(vpk_ctx* ctx, const double* lines, const double* segments, co
 /* Profiling runs only (vpk_profile_enable): accumulated algorithmic work of the weight-matrix
  * products (vp_localisation.py:515-524) since the last reset: out[0] = bytes of similarity
  * matrix consumed (8 N^2 per product), out[1] = flops (2 M N^2 per product), out[2] = number
- * of per-image products, out[3] = supersteps. */
-VPK_API int vpk_em_stats(vpk_ctx* ctx, uint64_t out[4], int reset);
+ * of per-image products, out[3] = supersteps, out[4] = algorithmic bytes of the POST kernel
+ * (the planes w, lvsq, pvl of every active image once per superstep: 8 (3 M N + 5 N)),
+ * out[5] = of the E-step kernel (same figure: three planes written). */
+VPK_API int vpk_em_stats(vpk_ctx* ctx, uint64_t out[6], int reset);
 
 /* ---- whole path ---------------------------------------------------------- */
 /* example.py:37-39 / benchmark.py:59-66 for a ragged batch, without the

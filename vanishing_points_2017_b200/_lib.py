@@ -135,10 +135,10 @@ class Context:
         check(self.lib.vpk_profile_reset(self.h), "vpk_profile_reset")
 
     def em_stats(self, reset=False):
-        out = (C.c_uint64 * 4)()
+        out = (C.c_uint64 * 6)()
         check(self.lib.vpk_em_stats(self.h, out, 1 if reset else 0), "vpk_em_stats")
         return {"wmat_bytes": int(out[0]), "wmat_flops": int(out[1]), "wmat_products": int(out[2]),
-                "supersteps": int(out[3])}
+                "supersteps": int(out[3]), "post_bytes": int(out[4]), "estep_bytes": int(out[5])}
 
     def profile_read(self):
         cap = 64

@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O2,-fvisibility=hidden,-ffp-contract=off",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
-]
+] + ["-D" + d for d in os.environ.get("VPK_DEFINES", "").split() if d]      # diagnostic builds, e.g. VPK_DEFINES=VPK_EM_MARKS
 
 
 def nvcc_path():

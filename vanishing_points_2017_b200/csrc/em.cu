@@ -27,6 +27,8 @@
 // decisions (counts < 3, argmax, err > 1.5, angle < thresh) sit on float values
 // and the parity gate is 1e-4 rad on the refined VPs.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include "em_core.cuh"
 #include "vpk_internal.cuh"
 
@@ -61,10 +63,13 @@ struct EmParams {
     EmSlot* slots;
     const SlotDesc* desc;
     double* ws;
-    int* lists;            // 2 x n_slots: active slot ids of the current / next superstep
-    int* ctl;              // [0],[1]: list lengths; [2]: overflow lock; [3]: supersteps done (parity = current list);
+    int* lists;            // 2 x n_slots: active slot ids of the current / next superstep, in slot order (heaviest image first)
+    int* alive;            // n_slots flags: the slot takes part in the next superstep
+    int* ctl;              // [0],[1]: list lengths; [3]: supersteps done (parity = current list);
                            // [4]: POST ticket counter; [5]: superstep limit hit
-    unsigned long long* stats;   // nullable (profiling): [0] algorithmic bytes, [1] flops of the W products, [2] slot-products
+    int* ovlock;           // lock of the overflow scratch (shared by all groups of a wave)
+    unsigned long long* stats;   // nullable (profiling): [0] algorithmic bytes, [1] flops of the W products, [2] slot-products,
+                                 // [3] algorithmic bytes of POST, [4] of the E-step
     int n_slots;
     double* overflow;
     size_t overflow_cap;
@@ -113,6 +118,17 @@ __device__ __forceinline__ void em_bulk_g2s(uint32_t dst, const void* src, uint3
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
+}
+
+// Stores of the per-superstep planes (lvsq, pvl, wt, w): kept in the L2 (evict-last) so that the next
+// kernel of the superstep reads them there although the similarity matrices stream through in between.
+__device__ __forceinline__ uint64_t em_policy_keep() {
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    return policy;
+}
+__device__ __forceinline__ void em_st_keep(double* p, double v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(policy) : "memory");
 }
 
 __device__ __forceinline__ void copy_slot(EmSlot* dst, const EmSlot* src, const Team& T) {
@@ -183,6 +199,40 @@ __global__ void __launch_bounds__(kPairThreads) em_pair_kernel(EmParams P) {
     }
 }
 
+// Closing of a kernel with one CTA per slot: every CTA has written alive[slot]; the last one to
+// arrive compacts the flags into list `next` IN SLOT ORDER (slots are sorted heaviest image first, so the
+// CTAs of the big images of the next E / W launches start first) and returns the number of active slots
+// to its thread 0 (-1 in every other CTA).  Block-wide; thread 0 of the last CTA resets the ticket.
+__device__ int close_slot_list(const EmParams& P, int next, const Team& T) {
+    __shared__ int s_last, s_warp[32], s_base;
+    __syncthreads();
+    if (T.tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(P.ctl + 4, 1) == (int)gridDim.x - 1;
+        s_base = 0;
+    }
+    __syncthreads();
+    if (!s_last) return -1;
+    __threadfence();
+    int* list = P.lists + next * P.n_slots;
+    for (int c0 = 0; c0 < P.n_slots; c0 += T.nthreads) {
+        const int i = c0 + T.tid;
+        const bool f = i < P.n_slots && *reinterpret_cast<volatile int*>(P.alive + i) != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (T.lane == 0) s_warp[T.warp] = __popc(bal);
+        __syncthreads();
+        int off = s_base, tot = 0;
+        for (int w = 0; w < T.nwarps; ++w) { if (w < T.warp) off += s_warp[w]; tot += s_warp[w]; }
+        if (f) list[off + __popc(bal & ((1u << T.lane) - 1u))] = i;
+        __syncthreads();
+        if (T.tid == 0) s_base += tot;
+        __syncthreads();
+    }
+    const int live = s_base;
+    if (T.tid == 0) { P.ctl[4] = 0; P.ctl[next] = live; }
+    return T.tid == 0 ? live : -1;
+}
+
 // ---------------------------------------------------------------------------
 // em_init: per-line constants, prior mixture, initial VPs, first E-step request
 // ---------------------------------------------------------------------------
@@ -210,7 +260,8 @@ __global__ void __launch_bounds__(kInitThreads) em_init_kernel(EmParams P) {
     const bool active = init_slot(st, isc, im, P.out, P.cfg, sph, P.S, iv, n_init, T);
     __syncthreads();
     copy_slot(P.slots + slot, &st, T);
-    if (active && T.tid == 0) P.lists[atomicAdd(P.ctl + 0, 1)] = slot;
+    if (T.tid == 0) P.alive[slot] = active ? 1 : 0;
+    close_slot_list(P, 0, T);
 }
 
 // ---------------------------------------------------------------------------
@@ -232,11 +283,14 @@ __global__ void __launch_bounds__(kEThreads) em_estep_kernel(EmParams P) {
     const int N = st.N, M = st.M, n0 = blockIdx.x * 32;
     if (n0 >= N) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // algorithmic bytes of this slot's E-step: segments + line weights in, the planes lvsq, pvl, wt out
+    if (P.stats && blockIdx.x == 0 && tid == 0) atomicAdd(P.stats + 4, 8ull * (5ull * N + 3ull * M * N));
     for (int m = tid; m < M; m += kEThreads) {
         c_pv[m] = st.pv[m]; c_vx[m] = st.vx[m]; c_vy[m] = st.vy[m]; c_inv2s[m] = st.inv2s[m]; c_coef[m] = st.coef[m];
     }
     __syncthreads();
     const Img im = make_img(N, P.ws + st.ws_off, P.segs + 4 * (size_t)st.base);
+    const uint64_t keep = em_policy_keep();
     const int n = n0 + lane;
     const bool live = n < N;
     const LineGeom g = line_geom(im.lp, live ? n : 0);
@@ -249,7 +303,7 @@ __global__ void __launch_bounds__(kEThreads) em_estep_kernel(EmParams P) {
         if (m < M) {
             double lvsq;
             estep_nm(g, c_vx[m], c_vy[m], c_inv2s[m], c_coef[m], lvsq, plv[mi]);
-            if (live) im.lvsq[(size_t)m * N + n] = lvsq;
+            if (live) em_st_keep(im.lvsq + (size_t)m * N + n, lvsq, keep);
             part += plv[mi] * c_pv[m];
         }
     }
@@ -269,7 +323,7 @@ __global__ void __launch_bounds__(kEThreads) em_estep_kernel(EmParams P) {
             double x = 0.0;
             if (m < M) {
                 x = plv[mi] * c_pv[m] * inv_pl;                         // calc_pvl (:128)
-                if (live) im.pvl[(size_t)m * N + n] = x;
+                if (live) em_st_keep(im.pvl + (size_t)m * N + n, x, keep);
                 x *= lw;                                                // weight_matrix :517
             }
             s_wt[p][lane][mm] = x;
@@ -280,7 +334,7 @@ __global__ void __launch_bounds__(kEThreads) em_estep_kernel(EmParams P) {
     for (int p = 0; p < passes; ++p) {
         const int ws = wpass_stride(M, p);
         double* dst = im.wt + (size_t)p * N * kMP + (size_t)n0 * ws;
-        for (int e = tid; e < nl * ws; e += kEThreads) dst[e] = s_wt[p][e / ws][e % ws];
+        for (int e = tid; e < nl * ws; e += kEThreads) em_st_keep(dst + e, s_wt[p][e / ws][e % ws], keep);
     }
 }
 
@@ -454,6 +508,7 @@ __global__ void __launch_bounds__(kWThreads, 2) em_wmat_kernel(EmParams P, int c
     __syncthreads();
     uint64_t policy;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    const uint64_t keep_policy = em_policy_keep();
     const int nchunks = (N + kJR - 1) / kJR;
     const int passes = (M + kMP - 1) / kMP;
     const double* slab = im.lsim + (size_t)t * N * kTK;
@@ -481,7 +536,9 @@ __global__ void __launch_bounds__(kWThreads, 2) em_wmat_kernel(EmParams P, int c
                 if (k < N && m < M) {
                     double sum = part[e];
                     for (int r = 1; r < cs; ++r) sum += em_ld_dsmem(part + e, (uint32_t)r);
-                    im.w[(size_t)m * N + k] = wmat_finish(im.wt[(size_t)pass * N * kMP + (size_t)k * ws + mm], im.lweight[k], im.colsum[k], sum, bias);
+                    em_st_keep(im.w + (size_t)m * N + k,
+                               wmat_finish(im.wt[(size_t)pass * N * kMP + (size_t)k * ws + mm], im.lweight[k], im.colsum[k], sum, bias),
+                               keep_policy);
                 }
             }
         }
@@ -500,30 +557,38 @@ __global__ void __launch_bounds__(kPostThreads) em_post_kernel(EmParams P, TierC
     __shared__ PostScratch sc;
     const int step = P.ctl[3], cur = step & 1;
     const Team T = make_team();
+#if defined(VPK_EM_MARKS)
+    if (T.tid == 0) { for (auto& m : sc.mark) m = 0; sc.mark_t = clock64(); }
+#endif
     if ((int)blockIdx.x < P.ctl[cur]) {
         const int slot = P.lists[cur * P.n_slots + blockIdx.x];
         copy_slot(&st, P.slots + slot, T);
         __syncthreads();
+        // algorithmic bytes of this slot's POST: the planes w, lvsq, pvl and the unit lines + weights once
+        if (P.stats && T.tid == 0) atomicAdd(P.stats + 3, 8ull * (3ull * st.M * st.N + 5ull * st.N));
         const Img im = make_img(st.N, P.ws + st.ws_off, P.segs + 4 * (size_t)st.base);
-        post_slot(st, sc, im, P.out, P.cfg, P.overflow, P.overflow_cap, P.ctl + 2, T);
+        post_slot(st, sc, im, P.out, P.cfg, P.overflow, P.overflow_cap, P.ovlock, T);
         __syncthreads();
+        VPK_MARK(sc, T, 6);
         copy_slot(P.slots + slot, &st, T);
-        if (T.tid == 0 && !st.done) P.lists[(cur ^ 1) * P.n_slots + atomicAdd(P.ctl + (cur ^ 1), 1)] = slot;
+        if (T.tid == 0) P.alive[slot] = st.done ? 0 : 1;
+        __syncthreads();
+        VPK_MARK(sc, T, 7);
+#if defined(VPK_EM_MARKS)
+        if (P.stats && T.tid == 0) {
+            for (int k = 0; k < 8; ++k) atomicAdd(P.stats + 8 + k, (unsigned long long)sc.mark[k]);
+            atomicAdd(P.stats + 16, 1ull);
+        }
+#endif
     }
     // the last block to finish closes the superstep: the other list becomes current, this one is emptied
-    __syncthreads();
-    if (T.tid == 0) {
-        __threadfence();
-        if (atomicAdd(P.ctl + 4, 1) == (int)gridDim.x - 1) {
-            __threadfence();
-            const int live = atomicAdd(P.ctl + (cur ^ 1), 0);
-            P.ctl[4] = 0;
-            P.ctl[cur] = 0;
-            P.ctl[3] = step + 1;
-            const bool stop = step + 1 >= tc.max_steps;
-            if (stop && live > 0) P.ctl[5] = 1;
-            for (int j = 0; j < tc.n; ++j) cudaGraphSetConditional(tc.h[j], (!stop && live > tc.thr[j]) ? 1u : 0u);
-        }
+    const int live = close_slot_list(P, cur ^ 1, T);
+    if (live >= 0) {
+        P.ctl[cur] = 0;
+        P.ctl[3] = step + 1;
+        const bool stop = step + 1 >= tc.max_steps;
+        if (stop && live > 0) P.ctl[5] = 1;
+        for (int j = 0; j < tc.n; ++j) cudaGraphSetConditional(tc.h[j], (!stop && live > tc.thr[j]) ? 1u : 0u);
     }
 }
 
@@ -546,31 +611,43 @@ struct EmLoopGraph {
     }
 };
 
+// A wave's slots are dealt to up to kMaxGroups groups, each running its own device-driven superstep
+// loop on its own stream: POST (one CTA per image, latency bound) of one group overlaps the W product
+// (HBM bound) of the others, and a group's tail of slow images does not hold the other groups back.
+constexpr int kMaxGroups = 8;
+constexpr int kGroupSlots = 26;       // images per group (default; VPK_EM_GROUPS overrides the group count)
+
 struct EmState {
-    DBuf ws, slots, desc, lists, ctl, stats, overflow, resp, out_small, out_assoc, out_dm, init_vp, init_off, sphere;
+    DBuf ws, slots, desc, lists, alive, ctl, stats, overflow, resp, out_small, out_assoc, out_dm, init_vp, init_off, sphere;
     HBuf h_desc, h_cnt;
-    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool attr_set = false;
-    EmLoopGraph* loop = nullptr;
+    EmLoopGraph* loop[kMaxGroups] = {};
+    cudaStream_t gstream[kMaxGroups] = {};
+    cudaEvent_t gdone[kMaxGroups] = {};
+    cudaEvent_t gev[kMaxGroups][8] = {};
+    cudaEvent_t fork = nullptr;
     int last_supersteps = 0;
-    unsigned long long totals[4] = {0, 0, 0, 0};   // accumulated W-product statistics + supersteps (profiling runs)
+    unsigned long long totals[6] = {0, 0, 0, 0, 0, 0};   // accumulated W-product statistics + supersteps (profiling runs)
 };
 
 void em_free(vpk_ctx* ctx) {
     if (!ctx->em) return;
     EmState* e = ctx->em;
-    e->ws.release(); e->slots.release(); e->desc.release(); e->lists.release(); e->ctl.release(); e->stats.release(); e->overflow.release();
+    e->ws.release(); e->slots.release(); e->desc.release(); e->lists.release(); e->alive.release(); e->ctl.release(); e->stats.release(); e->overflow.release();
     e->resp.release(); e->out_small.release(); e->out_assoc.release(); e->out_dm.release(); e->init_vp.release();
     e->init_off.release(); e->sphere.release(); e->h_desc.release(); e->h_cnt.release();
-    for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
-    if (e->loop) { e->loop->destroy(); delete e->loop; }
+    for (auto& l : e->loop) if (l) { l->destroy(); delete l; }
+    for (auto& g : e->gstream) if (g) cudaStreamDestroy(g);
+    for (auto& g : e->gdone) if (g) cudaEventDestroy(g);
+    for (auto& r : e->gev) for (auto& g : r) if (g) cudaEventDestroy(g);
+    if (e->fork) cudaEventDestroy(e->fork);
     delete e;
     ctx->em = nullptr;
 }
 
 // one superstep on the stream (direct launch or stream capture): E -> W -> POST over `bound` slots
-static int enqueue_superstep(vpk_ctx* ctx, const EmParams& P, int bound, int nmax, int csl, const TierCtl& tc, bool scoped) {
-    cudaStream_t sm = ctx->stream;
+static int enqueue_superstep(vpk_ctx* ctx, cudaStream_t sm, const EmParams& P, int bound, int nmax, int csl, const TierCtl& tc,
+                             bool scoped) {
     const int tiles = (nmax + kTK - 1) / kTK;
     {
         KernelScope ks(ctx, "em_estep", scoped);
@@ -603,7 +680,7 @@ static int enqueue_superstep(vpk_ctx* ctx, const EmParams& P, int bound, int nma
     return VPK_OK;
 }
 
-static int build_loop_graph(vpk_ctx* ctx, EmLoopGraph& G, const EmParams& P, int n, int nmax, int max_steps) {
+static int build_loop_graph(vpk_ctx* ctx, cudaStream_t sm, EmLoopGraph& G, const EmParams& P, int n, int nmax, int max_steps) {
     G.destroy();
     const int csl = wmat_split(nmax);
     VPK_CUDA(cudaGraphCreate(&G.graph, 0));
@@ -630,10 +707,10 @@ static int build_loop_graph(vpk_ctx* ctx, EmLoopGraph& G, const EmParams& P, int
         cudaGraphNode_t node;
         VPK_CUDA(cudaGraphAddNode(&node, G.graph, prev ? &prev : nullptr, prev ? 1 : 0, &np));
         cudaGraph_t body = np.conditional.phGraph_out[0];
-        VPK_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
-        int rc = enqueue_superstep(ctx, P, bound[j], nmax, csl, tc, false);
+        VPK_CUDA(cudaStreamBeginCaptureToGraph(sm, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+        int rc = enqueue_superstep(ctx, sm, P, bound[j], nmax, csl, tc, false);
         cudaGraph_t dummy = nullptr;
-        cudaError_t e = cudaStreamEndCapture(ctx->stream, &dummy);
+        cudaError_t e = cudaStreamEndCapture(sm, &dummy);
         if (rc != VPK_OK) return rc;
         VPK_CUDA(e);
         prev = node;
@@ -643,67 +720,124 @@ static int build_loop_graph(vpk_ctx* ctx, EmLoopGraph& G, const EmParams& P, int
     return VPK_OK;
 }
 
-// one wave: slots [0, n) described by h_desc (already in pinned memory)
-static int em_wave(vpk_ctx* ctx, EmState* st, EmParams& P, int n, int nmax) {
+// one wave: slots [0, n) described by h_desc (already in pinned memory); group g = slots [gstart[g], gstart[g+1])
+// with at most gnmax[g] segments each.  Every group runs its supersteps on its own stream, driven either
+// by a device-side loop graph (the default) or by the host (VPK_EM_HOST_LOOP=1 and profiling runs:
+// supersteps enqueued in chunks, the active count read LA chunks behind).
+static int em_wave(vpk_ctx* ctx, EmState* st, EmParams& P, int n, int G, const int* gstart, const int* gnmax, bool device_loop) {
     cudaStream_t sm = ctx->stream;
     VPK_CUDA(cudaMemcpyAsync(st->desc.p, st->h_desc.p, sizeof(SlotDesc) * (size_t)n, cudaMemcpyHostToDevice, sm));
-    VPK_CUDA(cudaMemsetAsync(st->ctl.p, 0, kCtlInts * sizeof(int), sm));
-    if (P.stats) VPK_CUDA(cudaMemsetAsync(P.stats, 0, 4 * sizeof(unsigned long long), sm));
-    P.n_slots = n;
-    const int tiles = (nmax + kTK - 1) / kTK;
-    const int csl = wmat_split(nmax);         // cluster size of the W launches (slots use min(wmat_split(N), csl))
+    VPK_CUDA(cudaMemsetAsync(st->ctl.p, 0, (kMaxGroups + 1) * kCtlInts * sizeof(int), sm));
+    if (P.stats) VPK_CUDA(cudaMemsetAsync(P.stats, 0, 32 * sizeof(unsigned long long), sm));
     const int max_steps = 64 * (P.cfg.num_iter + 8);
-    if (P.cfg.use_weights) {
-        KernelScope ks(ctx, "em_pair");
-        em_pair_kernel<<<dim3(tiles, n), kPairThreads, 0, sm>>>(P);
-        VPK_TRY(check_launch("em_pair"));
-    }
-    {
-        KernelScope ks(ctx, "em_init");
-        em_init_kernel<<<n, kInitThreads, 0, sm>>>(P);
-        VPK_TRY(check_launch("em_init"));
-    }
     int* h_cnt = st->h_cnt.as<int>();
-    static const bool host_loop = getenv("VPK_EM_HOST_LOOP") != nullptr;
-    if (!ctx->profiling && !host_loop) {
-        // ---- device-driven loop (no per-kernel events possible inside a graph: profiling runs use the host loop)
-        EmLoopGraph& G = *st->loop;
-        if (!G.exec || G.n != n || G.nmax != nmax || memcmp(&G.key, &P, sizeof(EmParams)) != 0)
-            VPK_TRY(build_loop_graph(ctx, G, P, n, nmax, max_steps));
-        VPK_CUDA(cudaGraphLaunch(G.exec, sm));
-        VPK_CUDA(cudaMemcpyAsync(h_cnt, P.ctl, kCtlInts * sizeof(int), cudaMemcpyDeviceToHost, sm));
-        VPK_CUDA(cudaStreamSynchronize(sm));
-        ctx->launches += 3 * (int64_t)h_cnt[3];
-        st->last_supersteps = h_cnt[3];
-        if (h_cnt[5]) { set_error("vpk_em: supersteps did not terminate"); return VPK_ERR_STATE; }
-        return VPK_OK;
-    }
-    // ---- host-driven loop: supersteps enqueued in chunks, the active count read LA chunks behind
-    TierCtl tc;
-    memset(&tc, 0, sizeof(tc));
-    tc.max_steps = max_steps;
-    int bound = n;              // upper bound of the number of active slots (they only ever finish)
-    int step = 0;
-    static const int LA = getenv("VPK_EM_LOOKAHEAD") ? atoi(getenv("VPK_EM_LOOKAHEAD")) : 3;
-    for (int chunk = 0;; ++chunk) {
-        if (chunk >= LA) {
-            VPK_CUDA(cudaEventSynchronize(st->ev[(chunk - LA) & 7]));
-            bound = h_cnt[8 + ((chunk - LA) & 7)];
-            if (bound <= 0) break;
+    static const bool trace = getenv("VPK_EM_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    int rebuilt = 0;
+    if (G > 1) VPK_CUDA(cudaEventRecord(st->fork, sm));
+
+    struct GroupRun { EmParams P; cudaStream_t s; int n, nmax, csl, bound, step; bool done; };
+    GroupRun R[kMaxGroups];
+    for (int g = 0; g < G; ++g) {
+        GroupRun& r = R[g];
+        r.s = G > 1 ? st->gstream[g] : sm;
+        if (G > 1) VPK_CUDA(cudaStreamWaitEvent(r.s, st->fork, 0));
+        memcpy(&r.P, &P, sizeof(EmParams));      // padding included: the loop graph is keyed on the bytes
+        const int g0 = gstart[g];
+        r.n = gstart[g + 1] - g0; r.nmax = gnmax[g]; r.csl = wmat_split(r.nmax); r.bound = r.n; r.step = 0; r.done = false;
+        r.P.slots = P.slots + g0; r.P.desc = P.desc + g0; r.P.lists = P.lists + 2 * (size_t)g0; r.P.alive = P.alive + g0;
+        r.P.ctl = P.ctl + g * kCtlInts; r.P.n_slots = r.n;
+        if (r.P.cfg.use_weights) {
+            KernelScope ks(ctx, "em_pair");
+            em_pair_kernel<<<dim3((r.nmax + kTK - 1) / kTK, r.n), kPairThreads, 0, r.s>>>(r.P);
+            VPK_TRY(check_launch("em_pair"));
         }
-        for (int k = 0; k < kChunkSteps; ++k, ++step) VPK_TRY(enqueue_superstep(ctx, P, bound, nmax, csl, tc, true));
-        // length of the list the next superstep will read
-        VPK_CUDA(cudaMemcpyAsync(h_cnt + 8 + (chunk & 7), P.ctl + (step & 1), sizeof(int), cudaMemcpyDeviceToHost, sm));
-        VPK_CUDA(cudaEventRecord(st->ev[chunk & 7], sm));
-        if (step > max_steps) { set_error("vpk_em: supersteps did not terminate"); return VPK_ERR_STATE; }
+        {
+            KernelScope ks(ctx, "em_init");
+            em_init_kernel<<<r.n, kInitThreads, 0, r.s>>>(r.P);
+            VPK_TRY(check_launch("em_init"));
+        }
+        if (device_loop) {
+            EmLoopGraph& L = *st->loop[g];
+            if (!L.exec || L.n != r.n || L.nmax != r.nmax || memcmp(&L.key, &r.P, sizeof(EmParams)) != 0) {
+                VPK_TRY(build_loop_graph(ctx, r.s, L, r.P, r.n, r.nmax, max_steps));
+                ++rebuilt;
+            }
+            VPK_CUDA(cudaGraphLaunch(L.exec, r.s));
+        }
     }
-    VPK_CUDA(cudaStreamSynchronize(sm));
-    st->last_supersteps = step;
+    int steps = 0;
+    if (device_loop) {
+        for (int g = 0; g < G && G > 1; ++g) {
+            VPK_CUDA(cudaEventRecord(st->gdone[g], R[g].s));
+            VPK_CUDA(cudaStreamWaitEvent(sm, st->gdone[g], 0));
+        }
+        VPK_CUDA(cudaMemcpyAsync(h_cnt, P.ctl, G * kCtlInts * sizeof(int), cudaMemcpyDeviceToHost, sm));
+        if (trace)
+            fprintf(stderr, "[vpk_em] enqueue %.3f ms\n",
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+        VPK_CUDA(cudaStreamSynchronize(sm));
+        for (int g = 0; g < G; ++g) {
+            const int* c = h_cnt + g * kCtlInts;
+            ctx->launches += 3 * (int64_t)c[3];
+            steps = std::max(steps, c[3]);
+            if (c[5]) { set_error("vpk_em: supersteps did not terminate"); return VPK_ERR_STATE; }
+        }
+    } else {
+        TierCtl tc;
+        memset(&tc, 0, sizeof(tc));
+        tc.max_steps = max_steps;
+        static const int LA = getenv("VPK_EM_LOOKAHEAD") ? std::max(1, std::min(7, atoi(getenv("VPK_EM_LOOKAHEAD")))) : 3;
+        int active = G;
+        for (int chunk = 0; active > 0; ++chunk) {
+            for (int g = 0; g < G; ++g) {
+                GroupRun& r = R[g];
+                if (r.done) continue;
+                int* ring = h_cnt + g * 8;
+                if (chunk >= LA) {
+                    VPK_CUDA(cudaEventSynchronize(st->gev[g][(chunk - LA) & 7]));
+                    r.bound = ring[(chunk - LA) & 7];     // upper bound of the number of active slots (they only ever finish)
+                    if (r.bound <= 0) {
+                        r.done = true;
+                        --active;
+                        if (G > 1) {
+                            VPK_CUDA(cudaEventRecord(st->gdone[g], r.s));
+                            VPK_CUDA(cudaStreamWaitEvent(sm, st->gdone[g], 0));
+                        }
+                        continue;
+                    }
+                }
+                for (int k = 0; k < kChunkSteps; ++k, ++r.step)
+                    VPK_TRY(enqueue_superstep(ctx, r.s, r.P, r.bound, r.nmax, r.csl, tc, true));
+                // length of the list the next superstep will read
+                VPK_CUDA(cudaMemcpyAsync(ring + (chunk & 7), r.P.ctl + (r.step & 1), sizeof(int), cudaMemcpyDeviceToHost, r.s));
+                VPK_CUDA(cudaEventRecord(st->gev[g][chunk & 7], r.s));
+                if (r.step > max_steps) { set_error("vpk_em: supersteps did not terminate"); return VPK_ERR_STATE; }
+            }
+        }
+        VPK_CUDA(cudaStreamSynchronize(sm));
+        for (int g = 0; g < G; ++g) steps = std::max(steps, R[g].step);
+    }
+    if (trace) {
+        const auto t_end = std::chrono::steady_clock::now();
+        fprintf(stderr, "[vpk_em] wave n=%d groups=%d %s loop, graphs rebuilt=%d, supersteps %d, %.3f ms\n", n, G,
+                device_loop ? "device" : "host", rebuilt, steps, std::chrono::duration<double, std::milli>(t_end - t_begin).count());
+    }
+    st->last_supersteps = steps;
     if (P.stats) {
-        unsigned long long h[4] = {0, 0, 0, 0};
-        VPK_CUDA(cudaMemcpy(h, P.stats, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        unsigned long long h[5] = {0, 0, 0, 0, 0};
+        VPK_CUDA(cudaMemcpy(h, P.stats, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         for (int k = 0; k < 3; ++k) st->totals[k] += h[k];
-        st->totals[3] += (unsigned long long)step;
+        st->totals[3] += (unsigned long long)steps;
+        st->totals[4] += h[3];
+        st->totals[5] += h[4];
+#if defined(VPK_EM_MARKS)
+        unsigned long long mk[9];
+        VPK_CUDA(cudaMemcpy(mk, P.stats + 8, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[vpk_em] POST cycles per slot-superstep (%llu):", mk[8]);
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " m%d=%.0f", k, (double)mk[k] / (double)std::max<unsigned long long>(mk[8], 1));
+        fprintf(stderr, "\n");
+#endif
     }
     return VPK_OK;
 }
@@ -719,7 +853,11 @@ int em_dev(vpk_ctx* ctx, const double* d_lines, const double* d_segments, const 
     if (!st->attr_set) {
         VPK_CUDA(cudaFuncSetAttribute(em_wmat_kernel<kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WSmemT<kStages>)));
         VPK_CUDA(cudaFuncSetAttribute(em_wmat_kernel<kStagesTail>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WSmemT<kStagesTail>)));
-        for (auto& ev : st->ev) VPK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto& ev : st->gdone) VPK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto& r : st->gev) for (auto& ev : r) VPK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        VPK_CUDA(cudaEventCreateWithFlags(&st->fork, cudaEventDisableTiming));
+        for (auto& g : st->gstream) VPK_CUDA(cudaStreamCreateWithFlags(&g, cudaStreamNonBlocking));
+        for (auto& l : st->loop) l = new EmLoopGraph();
         st->attr_set = true;
     }
     // heaviest images first
@@ -728,13 +866,21 @@ int em_dev(vpk_ctx* ctx, const double* d_lines, const double* d_segments, const 
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
         return (h_offsets[a + 1] - h_offsets[a]) > (h_offsets[b + 1] - h_offsets[b]);
     });
-    size_t free_b = 0, total_b = 0;
-    VPK_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t budget = std::max<size_t>((free_b + st->ws.cap) / 2, (size_t)1 << 28) / sizeof(double);
-    VPK_TRY(st->h_cnt.ensure(16 * sizeof(int)));
-    if (!st->loop) st->loop = new EmLoopGraph();
-    VPK_TRY(st->ctl.ensure(kCtlInts * sizeof(int)));
-    VPK_TRY(st->stats.ensure(4 * sizeof(unsigned long long)));
+    // workspace budget of a wave: the whole batch if the workspace already holds it (no driver query on
+    // the steady-state path), else half of what is free
+    size_t all_doubles = 0;
+    for (int b = 0; b < B; ++b) all_doubles += slot_doubles(h_offsets[b + 1] - h_offsets[b]);
+    size_t budget = all_doubles;
+    if (all_doubles * sizeof(double) > st->ws.cap) {
+        size_t free_b = 0, total_b = 0;
+        VPK_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        budget = std::max<size_t>((free_b + st->ws.cap) / 2, (size_t)1 << 28) / sizeof(double);
+    }
+    static const bool trace_dev = getenv("VPK_EM_TRACE") != nullptr;
+    const auto t_dev0 = std::chrono::steady_clock::now();
+    VPK_TRY(st->h_cnt.ensure(kMaxGroups * 8 * sizeof(int)));
+    VPK_TRY(st->ctl.ensure((kMaxGroups + 1) * kCtlInts * sizeof(int)));
+    VPK_TRY(st->stats.ensure(32 * sizeof(unsigned long long)));
 
     EmParams P;
     memset(&P, 0, sizeof(P));                   // padding included: the loop graph is keyed on the bytes
@@ -764,22 +910,43 @@ int em_dev(vpk_ctx* ctx, const double* d_lines, const double* d_segments, const 
         VPK_TRY(st->slots.ensure(sizeof(EmSlot) * (size_t)n));
         VPK_TRY(st->desc.ensure(sizeof(SlotDesc) * (size_t)n));
         VPK_TRY(st->lists.ensure(2 * sizeof(int) * (size_t)n));
+        VPK_TRY(st->alive.ensure(sizeof(int) * (size_t)n));
         const size_t ov = (size_t)nmax * nmax + 6 * (size_t)nmax + 16;
         VPK_TRY(st->overflow.ensure(ov * sizeof(double)));
         VPK_TRY(st->h_desc.ensure(sizeof(SlotDesc) * (size_t)n));
         SlotDesc* hd = st->h_desc.as<SlotDesc>();
+        // groups: the wave's images (heaviest first) are dealt round-robin, so every group gets the same
+        // mix of sizes; a group's slots are contiguous.  One group per ~kGroupSlots images.
+        static const int env_groups = getenv("VPK_EM_GROUPS") ? atoi(getenv("VPK_EM_GROUPS")) : 0;
+        static const bool host_loop_env = getenv("VPK_EM_HOST_LOOP") != nullptr;
+        const bool device_loop = !host_loop_env && !ctx->profiling;   // no per-kernel events inside a graph
+        int G = env_groups > 0 ? env_groups : (n + kGroupSlots - 1) / kGroupSlots;
+        G = std::max(1, std::min(G, std::min(n, kMaxGroups)));
+        if (ctx->profiling) G = 1;          // per-kernel events are recorded on the context's stream
+        int gstart[kMaxGroups + 1], gnmax[kMaxGroups];
         size_t off = 0;
-        for (int i = 0; i < n; ++i) {
-            const int b = order[begin + i];
-            hd[i].img = b; hd[i].base = h_offsets[b]; hd[i].N = h_offsets[b + 1] - h_offsets[b]; hd[i].pad = 0;
-            hd[i].ws_off = off;
-            off += slot_doubles(hd[i].N);
+        int i = 0;
+        for (int g = 0; g < G; ++g) {
+            gstart[g] = i;
+            gnmax[g] = 1;
+            for (int k = g; k < n; k += G, ++i) {
+                const int b = order[begin + k];
+                hd[i].img = b; hd[i].base = h_offsets[b]; hd[i].N = h_offsets[b + 1] - h_offsets[b]; hd[i].pad = 0;
+                hd[i].ws_off = off;
+                off += slot_doubles(hd[i].N);
+                gnmax[g] = std::max(gnmax[g], hd[i].N);
+            }
         }
+        gstart[G] = n;
         P.slots = st->slots.as<EmSlot>(); P.desc = st->desc.as<SlotDesc>(); P.ws = st->ws.as<double>();
-        P.lists = st->lists.as<int>(); P.ctl = st->ctl.as<int>();
+        P.lists = st->lists.as<int>(); P.alive = st->alive.as<int>(); P.ctl = st->ctl.as<int>();
+        P.ovlock = st->ctl.as<int>() + kMaxGroups * kCtlInts;
         P.stats = ctx->profiling ? st->stats.as<unsigned long long>() : nullptr;
         P.overflow = st->overflow.as<double>(); P.overflow_cap = ov;
-        VPK_TRY(em_wave(ctx, st, P, n, nmax));
+        if (trace_dev)
+            fprintf(stderr, "[vpk_em] host set-up %.3f ms\n",
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_dev0).count());
+        VPK_TRY(em_wave(ctx, st, P, n, G, gstart, gnmax, device_loop));
         begin = end;
     }
     return VPK_OK;
@@ -791,9 +958,9 @@ using namespace vpk;
 
 extern "C" {
 
-int vpk_em_stats(vpk_ctx* ctx, uint64_t out[4], int reset) {
+int vpk_em_stats(vpk_ctx* ctx, uint64_t out[6], int reset) {
     if (!ctx || !out) { set_error("vpk_em_stats: bad argument"); return VPK_ERR_ARG; }
-    for (int k = 0; k < 4; ++k) out[k] = ctx->em ? ctx->em->totals[k] : 0;
+    for (int k = 0; k < 6; ++k) out[k] = ctx->em ? ctx->em->totals[k] : 0;
     if (reset && ctx->em) for (auto& t : ctx->em->totals) t = 0;
     return VPK_OK;
 }

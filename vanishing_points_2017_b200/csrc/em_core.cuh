@@ -416,7 +416,15 @@ struct PostScratch {
     int ok[kMaxM], rem[kMaxM];
     int ia, ib, flag;
     double da;
+#if defined(VPK_EM_MARKS)
+    long long mark[16], mark_t;        // cycles of thread 0 between the markers of post_slot (diagnostic builds)
+#endif
 };
+#if defined(__CUDACC__) && defined(VPK_EM_MARKS)
+#define VPK_MARK(sc, T, k) do { if ((T).tid == 0) { long long c_ = clock64(); (sc).mark[k] += c_ - (sc).mark_t; (sc).mark_t = c_; } } while (0)
+#else
+#define VPK_MARK(sc, T, k) do {} while (0)
+#endif
 
 // Block-wide arg-min of (v, i) pairs: smallest v, ties -> smallest i; i < 0 = no candidate.
 // Result in sc.da / sc.ia (ia < 0: no candidate at all).  Deterministic.
@@ -746,17 +754,10 @@ struct RefitAcc {
 VPK_DEVFN void refit_sums(const Img& im, const double* wrow, const double* wrow2, int sel, int vm, int vm2, RefitAcc& acc,
                           const Team& T) {
     const int N = im.N;
+    // One sweep: the row maximum and the unscaled sums side by side; the scatter matrix of the rows
+    // (w / max w) l is the unscaled one times 1 / (max w)^2 (rounding-level difference, same eigenvectors).
     double mx = -INFINITY;
     bool any = false;
-#pragma unroll 4
-    for (int n = T.lane; n < N; n += T.lanes) {
-        const double x = wrow[n] + (wrow2 ? wrow2[n] : 0.0);
-        const bool use = sel < 0 || im.assoc[n] == sel;
-        if (use) { any = true; mx = nanmax(mx, x); }
-    }
-    mx = warp_max_nanprop(mx);
-    any = warp_any(any);
-    const bool fit = !(!any || mx == 0.0 || isnan(mx) || isinf(mx));     // :456-460 / LinAlgError
     const double* p1 = im.pvl + (size_t)vm * N;
     const double* q1 = im.lvsq + (size_t)vm * N;
     const double* p2 = vm2 >= 0 ? im.pvl + (size_t)vm2 * N : nullptr;
@@ -770,16 +771,36 @@ VPK_DEVFN void refit_sums(const Img& im, const double* wrow, const double* wrow2
         if (p2) { p += p2[n]; q = 0.5 * (q2[n] + q); }
         num += q * p;
         den += p;
-        const double wv = wrow[n] + (wrow2 ? wrow2[n] : 0.0);
+        const double x = wrow[n] + (wrow2 ? wrow2[n] : 0.0);
         const double l0 = im.ln[3 * (size_t)n], l1 = im.ln[3 * (size_t)n + 1], l2 = im.ln[3 * (size_t)n + 2];
-        const bool use = fit && (sel < 0 || im.assoc[n] == sel);
+        const bool use = sel < 0 || im.assoc[n] == sel;
         if (use) {
-            const double x = wv / mx;
+            any = true;
+            mx = nanmax(mx, x);
             const double a = x * l0, b = x * l1, c = x * l2;
             g[0] += a * a; g[1] += a * b; g[2] += a * c; g[3] += b * b; g[4] += b * c; g[5] += c * c;
             ++rows; only = n;
         }
     }
+    mx = warp_max_nanprop(mx);
+    any = warp_any(any);
+    const bool fit = !(!any || mx == 0.0 || isnan(mx) || isinf(mx));     // :456-460 / LinAlgError
+    if (fit && (mx < 1e-140 || mx > 1e140)) {
+        // the squares would leave the float64 range: scale the rows first (second sweep, rare)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) g[k] = 0.0;
+        for (int n = T.lane; n < N; n += T.lanes) {
+            if (!(sel < 0 || im.assoc[n] == sel)) continue;
+            const double x = (wrow[n] + (wrow2 ? wrow2[n] : 0.0)) / mx;
+            const double a = x * im.ln[3 * (size_t)n], b = x * im.ln[3 * (size_t)n + 1], c = x * im.ln[3 * (size_t)n + 2];
+            g[0] += a * a; g[1] += a * b; g[2] += a * c; g[3] += b * b; g[4] += b * c; g[5] += c * c;
+        }
+    } else {
+        const double inv = fit ? 1.0 / mx : 0.0, inv2 = inv * inv;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) g[k] *= inv2;
+    }
+    if (!fit) rows = 0;
     num = warp_sum(num);
     den = warp_sum(den);
 #pragma unroll
@@ -1226,6 +1247,7 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
     const int N = im.N;
     const double max_stdd = 1e-6;            // angle mode (:197)
     int ph = st.phase;
+    VPK_MARK(sc, T, 0);
     while (true) {
         team_sync();
         switch (ph) {
@@ -1247,6 +1269,7 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
                 request(st, 0, PH_SPLIT, T);
                 return;
             }
+            VPK_MARK(sc, T, 5);
             request(st, 0, PH_MSTEP, T);                       // :273, :282
             return;
         }
@@ -1263,8 +1286,12 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
             const int M = st.M;
             RefitAcc* acc = refit_acc(sc);
             if (cfg.do_iterations) {
+                VPK_MARK(sc, T, 1);
                 for (int m = T.warp; m < M; m += T.nwarps) refit_sums(im, im.w + (size_t)m * N, nullptr, -1, m, -1, acc[m], T);
+                team_sync();
+                VPK_MARK(sc, T, 2);
                 refit_finish(acc, M, T);
+                VPK_MARK(sc, T, 3);
             }
             for (int m = T.tid; m < M; m += T.nthreads) {
                 if (!cfg.do_iterations) {
@@ -1314,6 +1341,7 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
                 st.s[m] = sm;
             }
             team_sync();
+            VPK_MARK(sc, T, 4);
             const int i = st.iter;
             if (max_err < cfg.final_convergence || i == cfg.num_iter - 1 || !cfg.do_iterations) {   // :335
                 if (cfg.do_merge) {                                                  // :339
