@@ -29,7 +29,7 @@ struct CnnState {
     bool has_mean = false;
     // activations (sized for `cap` images)
     int cap = 0;
-    DBuf a1, c1, a2, c2, a3, a4, a5, c5, a6, f6, f7, logits, sig, img;
+    DBuf a1, c1, a2, c2, a3, a4, a5, c5, a6, f6, f7, logits, sig, img, splitk;
 };
 
 void cnn_free(vpk_ctx* ctx) {
@@ -37,7 +37,7 @@ void cnn_free(vpk_ctx* ctx) {
     CnnState* s = ctx->cnn;
     for (int i = 0; i < 8; ++i) { s->w[i].release(); s->b[i].release(); }
     s->mean.release();
-    DBuf* bufs[] = {&s->a1, &s->c1, &s->a2, &s->c2, &s->a3, &s->a4, &s->a5, &s->c5, &s->a6, &s->f6, &s->f7, &s->logits, &s->sig, &s->img};
+    DBuf* bufs[] = {&s->a1, &s->c1, &s->a2, &s->c2, &s->a3, &s->a4, &s->a5, &s->c5, &s->a6, &s->f6, &s->f7, &s->logits, &s->sig, &s->img, &s->splitk};
     for (DBuf* d : bufs) d->release();
     delete s;
     ctx->cnn = nullptr;
@@ -241,7 +241,12 @@ int launch_gemm(vpk_ctx* ctx, const GemmCall& c) {
     VPK_TRY(make_map(st, &mb, c.B, c.b_inner, c.b_rows, c.b_inner * 2, (uint32_t)c.p.bn));
     const int m_tiles = (c.p.m_total + kBM - 1) / kBM;
     const int n_tiles = (c.p.n_valid + c.p.bn - 1) / c.p.bn;
-    dim3 grid(m_tiles, n_tiles, c.groups);
+    const int ksplit = c.p.ksplit > 1 ? c.p.ksplit : 1;
+    if (ksplit > 1 && ((ksplit - 1) * ((c.p.k_blocks + ksplit - 1) / ksplit) >= c.p.k_blocks || !c.p.partial)) {
+        set_error("%s: bad split-K configuration", c.name);
+        return VPK_ERR_ARG;
+    }
+    dim3 grid(m_tiles, n_tiles, c.groups * ksplit);
     const size_t stage = kABytes + (size_t)c.p.bn * kBK * 2;
     KernelScope ks(ctx, c.name);
     if (c.p.bn <= 128) {
@@ -256,6 +261,22 @@ int launch_gemm(vpk_ctx* ctx, const GemmCall& c) {
         gemm_bf16_tcgen05_kernel<4><<<grid, kGemmThreads, smem, ctx->stream>>>(ma, mb, c.p);
     }
     return check_launch(c.name);
+}
+
+// plain GEMM (m x n x k) with the K range dealt to `ksplit` CTAs per output tile + the finishing pass
+static int launch_gemm_splitk(vpk_ctx* ctx, GemmCall c, int ksplit, const char* finish_name) {
+    if (ksplit <= 1) return launch_gemm(ctx, c);
+    CnnState* s = ctx->cnn;
+    const int M = c.p.m_total, N = c.p.n_valid, ld = c.p.ldc;
+    const long long stride = (long long)M * ld;
+    VPK_TRY(s->splitk.ensure((size_t)ksplit * stride * sizeof(float)));
+    c.p.ksplit = ksplit; c.p.partial = s->splitk.as<float>(); c.p.partial_stride = stride;
+    VPK_TRY(launch_gemm(ctx, c));
+    KernelScope ks(ctx, finish_name);
+    const long long t = (long long)M * (N / 4);
+    splitk_finish_kernel<<<(unsigned)((t + 255) / 256), 256, 0, ctx->stream>>>(c.p.partial, ksplit, stride, M, N, ld, c.p.bias, c.p.relu,
+                                                                             c.p.out_f32, c.p.out);
+    return check_launch(finish_name);
 }
 
 static GemmParams plain_params(int m, int n, int k, int bn, int ldc, const float* bias, int relu, int out_f32, void* out) {
@@ -392,16 +413,16 @@ int cnn_forward_dev(vpk_ctx* ctx, const uint8_t* d_images, int32_t n, float* d_s
     c.name = "gemm_fc6"; c.A = s->a6.p; c.a_inner = 57600; c.a_rows = n; c.a_pitch = 57600 * 2;
     c.B = s->w[5].p; c.b_inner = 57600; c.b_rows = 4096; c.groups = 1;
     c.p = plain_params(n, 4096, 57600, 256, 4096, s->b[5].as<float>(), 1, 0, s->f6.p);
-    VPK_TRY(launch_gemm(ctx, c));
+    VPK_TRY(launch_gemm_splitk(ctx, c, n <= 256 ? 9 : 1, "splitk_fc6"));
     c.name = "gemm_fc7"; c.A = s->f6.p; c.a_inner = 4096; c.a_rows = n; c.a_pitch = 8192;
     c.B = s->w[6].p; c.b_inner = 4096; c.b_rows = 4096;
     c.p = plain_params(n, 4096, 4096, 256, 4096, s->b[6].as<float>(), 1, 0, s->f7.p);
-    VPK_TRY(launch_gemm(ctx, c));
+    VPK_TRY(launch_gemm_splitk(ctx, c, n <= 256 ? 8 : 1, "splitk_fc7"));
     float* logits = d_logits ? d_logits : s->logits.as<float>();
     c.name = "gemm_fc8"; c.A = s->f7.p; c.a_inner = 4096; c.a_rows = n; c.a_pitch = 8192;
     c.B = s->w[7].p; c.b_inner = 4096; c.b_rows = 400;
     c.p = plain_params(n, 400, 4096, 80, 400, s->b[7].as<float>(), 0, 1, logits);
-    VPK_TRY(launch_gemm(ctx, c));
+    VPK_TRY(launch_gemm_splitk(ctx, c, n <= 256 ? 16 : 1, "splitk_fc8"));
     if (d_sigout) {
         KernelScope ks(ctx, "sigmoid");
         long long t = (long long)n * 400;

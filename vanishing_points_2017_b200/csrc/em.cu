@@ -576,8 +576,8 @@ __global__ void __launch_bounds__(kPostThreads) em_post_kernel(EmParams P, TierC
         VPK_MARK(sc, T, 7);
 #if defined(VPK_EM_MARKS)
         if (P.stats && T.tid == 0) {
-            for (int k = 0; k < 8; ++k) atomicAdd(P.stats + 8 + k, (unsigned long long)sc.mark[k]);
-            atomicAdd(P.stats + 16, 1ull);
+            for (int k = 0; k < 10; ++k) atomicAdd(P.stats + 8 + k, (unsigned long long)sc.mark[k]);
+            atomicAdd(P.stats + 18, 1ull);
         }
 #endif
     }
@@ -832,10 +832,10 @@ static int em_wave(vpk_ctx* ctx, EmState* st, EmParams& P, int n, int G, const i
         st->totals[4] += h[3];
         st->totals[5] += h[4];
 #if defined(VPK_EM_MARKS)
-        unsigned long long mk[9];
-        VPK_CUDA(cudaMemcpy(mk, P.stats + 8, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[vpk_em] POST cycles per slot-superstep (%llu):", mk[8]);
-        for (int k = 0; k < 8; ++k) fprintf(stderr, " m%d=%.0f", k, (double)mk[k] / (double)std::max<unsigned long long>(mk[8], 1));
+        unsigned long long mk[11];
+        VPK_CUDA(cudaMemcpy(mk, P.stats + 8, 11 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[vpk_em] POST cycles per slot-superstep (%llu):", mk[10]);
+        for (int k = 0; k < 10; ++k) fprintf(stderr, " m%d=%.0f", k, (double)mk[k] / (double)std::max<unsigned long long>(mk[10], 1));
         fprintf(stderr, "\n");
 #endif
     }

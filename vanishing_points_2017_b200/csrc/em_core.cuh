@@ -1199,10 +1199,17 @@ VPK_DEVFN void write_result(const EmOut& out, const Img& im, EmSlot& st, int sta
 }
 
 // ask for an E-step (and weight matrix) on cur (vsel 0) or nxt (vsel 1); POST resumes in `phase`
-VPK_DEVFN void request(EmSlot& st, int vsel, int phase, const Team& T) {
+VPK_DEVFN void request(EmSlot& st, int vsel, int phase, const Team& T, PostScratch* msc = nullptr) {
     team_sync();
     if (T.tid == 0) { st.vsel = vsel; st.phase = phase; st.run_e = 1; st.run_w = 1; }
+#if defined(VPK_EM_MARKS)
+    if (msc) VPK_MARK(*msc, T, 8);
+#endif
     prepare_estep(st, vsel ? st.nxt : st.cur, T);
+#if defined(VPK_EM_MARKS)
+    if (msc) VPK_MARK(*msc, T, 9);
+#endif
+    (void)msc;
 }
 
 // ---------------------------------------------------------------------------
@@ -1266,11 +1273,11 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
                 return;
             }
             if (i % cfg.split_merge_freq == 0 && i > 0 && i < 100 && cfg.do_split) {     // :262
-                request(st, 0, PH_SPLIT, T);
+                request(st, 0, PH_SPLIT, T, &sc);
                 return;
             }
             VPK_MARK(sc, T, 5);
-            request(st, 0, PH_MSTEP, T);                       // :273, :282
+            request(st, 0, PH_MSTEP, T, &sc);                       // :273, :282
             return;
         }
         case PH_SPLIT: {
@@ -1278,7 +1285,7 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
             // no candidate: the E/W results of this superstep are exactly what :273/:282 recompute
             if (changed < 0) { ph = PH_MSTEP; break; }
             // otherwise the split scratch has overwritten lvsq/pvl/w
-            request(st, 0, PH_MSTEP, T);
+            request(st, 0, PH_MSTEP, T, &sc);
             return;
         }
         case PH_MSTEP: {
@@ -1390,7 +1397,7 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
             }
             if (!(sc.da < st.merge_thresh)) { ph = st.after_merge; break; }
             if (T.tid == 0) { st.merge_j = sc.ia; st.merge_k = sc.ib; }
-            request(st, 1, PH_MERGE_EVAL, T);
+            request(st, 1, PH_MERGE_EVAL, T, &sc);
             return;
         }
         case PH_MERGE_EVAL: {
@@ -1421,7 +1428,7 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
             break;
         }
         case CT_FINAL_A: {
-            request(st, 0, PH_HARD_REFIT, T);                   // :344 (index i, sic)
+            request(st, 0, PH_HARD_REFIT, T, &sc);                   // :344 (index i, sic)
             return;
         }
         case PH_HARD_REFIT: {
@@ -1455,7 +1462,7 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
                 write_result(out, im, st, VPK_EM_NO_VPS_LEFT, 0, false, T);
                 return;
             }
-            request(st, 0, PH_KEEP_WINNERS, T);                 // :398
+            request(st, 0, PH_KEEP_WINNERS, T, &sc);                 // :398
             return;
         }
         case PH_KEEP_WINNERS: {
@@ -1466,7 +1473,7 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
             for (int n = T.tid; n < N; n += T.nthreads) sc.rem[im.assoc[n]] = 0;
             compact_vps(st, sc.rem, T);
             if (T.tid == 0) st.vidx = 0;
-            request(st, 1, PH_FINAL_COUNTS, T);                 // :415 (index i+1)
+            request(st, 1, PH_FINAL_COUNTS, T, &sc);                 // :415 (index i+1)
             return;
         }
         case PH_FINAL_COUNTS: {
@@ -1490,7 +1497,7 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
                 write_result(out, im, st, VPK_EM_NO_VPS_LEFT, st.iter, false, T);
                 return;
             }
-            request(st, 1, PH_FINAL_COUNTS, T);
+            request(st, 1, PH_FINAL_COUNTS, T, &sc);
             return;
         }
         default:

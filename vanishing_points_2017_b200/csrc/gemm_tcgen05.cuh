@@ -17,6 +17,7 @@
 // is selected by advancing the descriptor start address.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -46,6 +47,12 @@ struct GemmParams {
     int bn;                                // N tile (multiple of 16, <= 256)
     const float* bias;                     // [groups * n_valid] or nullptr
     void* out;
+    // ---- split-K (plain GEMMs with few output tiles: the K range is dealt to ksplit CTAs per tile,
+    // each writes its raw fp32 partial tile to partial + split * partial_stride; splitk_finish_kernel
+    // adds them in split order, then bias / ReLU / conversion).  ksplit <= 1: off.
+    int ksplit;
+    float* partial;
+    long long partial_stride;
 };
 
 // ---- PTX wrappers -----------------------------------------------------------
@@ -133,7 +140,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const uint32_t sA = sbase, sB = sbase + kStages * kABytes;
     const int m0 = blockIdx.x * kBM;
     const int n0 = blockIdx.y * p.bn;
-    const int g = blockIdx.z;
+    const int nsplit = p.ksplit > 1 ? p.ksplit : 1;
+    const int g = blockIdx.z / nsplit, ksp = blockIdx.z - g * nsplit;
+    const int kb_per = (p.k_blocks + nsplit - 1) / nsplit;
+    const int kb0 = ksp * kb_per, nkb = min(kb_per, p.k_blocks - kb0);       // host guarantees nkb >= 1
     uint32_t ncols = 32;
     while ((int)ncols < p.bn) ncols <<= 1;
 
@@ -156,9 +166,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
-            for (int kb = 0; kb < p.k_blocks; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+            for (int i = 0; i < nkb; ++i) {
+                const int kb = kb0 + i;
+                const int s = i % kStages;
+                const uint32_t ph = (uint32_t)(i / kStages) & 1u;
                 mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
                 const uint32_t full = smem_u32(&bar_full[s]);
                 mbar_expect_tx(full, kABytes + b_bytes);
@@ -171,9 +182,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     } else if (warp == 1) {
         // ===== MMA issuer =====
         const uint32_t idesc = umma_idesc_bf16(kBM, p.bn);
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
-            const int s = kb % kStages;
-            const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % kStages;
+            const uint32_t ph = (uint32_t)(i / kStages) & 1u;
             mbar_wait(smem_u32(&bar_full[s]), ph);
             tcgen05_fence_after();
             if (lane == 0) {
@@ -181,10 +192,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 for (int k = 0; k < kBK / 16; ++k) {
                     uint64_t ad = umma_desc_sw128(sA + s * kABytes + k * 32);
                     uint64_t bd = umma_desc_sw128(sB + s * b_bytes + k * 32);
-                    tcgen05_mma_bf16(tmem, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                    tcgen05_mma_bf16(tmem, ad, bd, idesc, (i | k) ? 1u : 0u);
                 }
                 tcgen05_commit(smem_u32(&bar_empty[s]));        // frees the smem stage when the MMAs retire
-                if (kb == p.k_blocks - 1) tcgen05_commit(smem_u32(&bar_acc));
+                if (i == nkb - 1) tcgen05_commit(smem_u32(&bar_acc));
             }
             __syncwarp();
         }
@@ -208,6 +219,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             uint32_t r[16];
             tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
             if (!valid || n0 + c >= p.n_valid) continue;
+            if (p.ksplit > 1) {
+                float4* o = reinterpret_cast<float4*>(p.partial + (long long)ksp * p.partial_stride + orow * p.ldc + ccol0 + c);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                       __uint_as_float(r[4 * j + 3]));
+                continue;
+            }
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -237,6 +256,32 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols) : "memory");
+    }
+}
+
+// out[m, n] = act(bias[n] + sum_s partial[s][m][n]), splits added in order (deterministic)
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ partial, int ksplit, long long stride, int M,
+                                                            int N, int ld, const float* __restrict__ bias, int relu, int out_f32,
+                                                            void* __restrict__ out) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int nq = N >> 2;
+    if (t >= (long long)M * nq) return;
+    const int m = (int)(t / nq), n = (int)(t - (long long)m * nq) * 4;
+    const float* src = partial + (long long)m * ld + n;
+    float4 a = *reinterpret_cast<const float4*>(src);
+    for (int s = 1; s < ksplit; ++s) {
+        const float4 b = *reinterpret_cast<const float4*>(src + s * stride);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (bias) { a.x += bias[n]; a.y += bias[n + 1]; a.z += bias[n + 2]; a.w += bias[n + 3]; }
+    if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+    if (out_f32) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (long long)m * ld + n) = a;
+    } else {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&lo); o.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + (long long)m * ld + n) = o;
     }
 }
 
