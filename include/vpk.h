@@ -98,9 +98,11 @@ VPK_API int vpk_cnn_forward(vpk_ctx* ctx, const uint8_t* images, int32_t n_image
 
 /* Diagnostics: one plain GEMM out = act(a * b^T + bias) through the tcgen05 kernel every
  * CNN layer uses.  a (m,k) and b (n,k) are bf16 bit patterns, out (m,n) float32;
- * k % 64 == 0, bn % 16 == 0, 16 <= bn <= 256, n % bn == 0. */
+ * k % 64 == 0, bn % 16 == 0, 16 <= bn <= 256, n % bn == 0.  ksplit > 1: the K range is dealt to
+ * ksplit CTAs per output tile and a finishing pass adds the partial tiles in order (how the fully
+ * connected layers run for batches of up to 256 images); ksplit = 1: one CTA per tile. */
 VPK_API int vpk_debug_gemm(vpk_ctx* ctx, int32_t m, int32_t n, int32_t k, const uint16_t* a, const uint16_t* b,
-                           const float* bias, int32_t relu, int32_t bn, float* out);
+                           const float* bias, int32_t relu, int32_t bn, int32_t ksplit, float* out);
 
 /* ---- E0..E12: EM --------------------------------------------------------- */
 /* keyword arguments of vp_localisation.expectation_maximisation

@@ -24,14 +24,17 @@ def bf16_bits(x):
     return t.view(torch.int16).numpy().view(np.uint16), t.to(torch.float32).numpy()
 
 
-@pytest.mark.parametrize("m,n,k,bn", [(128, 128, 64, 128), (128, 256, 256, 256), (300, 384, 1024, 128),
-                                      (77, 192, 192, 192), (1, 400, 4096, 80), (515, 96, 192, 96)])
-def test_gemm_tcgen05(cnn, m, n, k, bn):
+@pytest.mark.parametrize("m,n,k,bn,ksplit", [(128, 128, 64, 128, 1), (128, 256, 256, 256, 1), (300, 384, 1024, 128, 1),
+                                             (77, 192, 192, 192, 1), (1, 400, 4096, 80, 1), (515, 96, 192, 96, 1),
+                                             # split-K as the fully connected layers use it (fc6: K = 57600, 9 splits)
+                                             (102, 512, 57600, 256, 9), (102, 4096, 4096, 256, 8), (7, 400, 4096, 80, 16),
+                                             (300, 256, 640, 128, 3), (102, 256, 704, 256, 4)])
+def test_gemm_tcgen05(cnn, m, n, k, bn, ksplit):
     rs = np.random.RandomState(m + n + k)
     a_bits, a = bf16_bits(rs.standard_normal((m, k)).astype(np.float32))
     b_bits, b = bf16_bits(rs.standard_normal((n, k)).astype(np.float32))
     bias = rs.standard_normal(n).astype(np.float32)
-    out = cnn.debug_gemm(a_bits, b_bits, bias=bias, relu=True, bn=bn)
+    out = cnn.debug_gemm(a_bits, b_bits, bias=bias, relu=True, bn=bn, ksplit=ksplit)
     ref = np.maximum(a.astype(np.float64) @ b.astype(np.float64).T + bias, 0)
     np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-3 * np.sqrt(k))
 

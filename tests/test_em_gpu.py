@@ -88,6 +88,34 @@ def test_batch_matches_single_and_handles_empty(em):
         np.testing.assert_array_equal(out[b]["vp_assoc"], single["vp_assoc"])
 
 
+def test_grouped_batch_matches_single(em):
+    """70 images are dealt to three groups whose superstep loops run concurrently on their own
+    streams; every image's result must be bit-identical to the same image run alone."""
+    rs = np.random.RandomState(77)
+    ns = [int(n) for n in rs.randint(30, 170, size=70)]
+    scs = [synth.make_scene(1200 + i, n, noise_deg=0.5 + (i % 3)) for i, n in enumerate(ns)]
+    segs = [s["segments"] for s in scs]
+    lines = [s["lines"] for s in scs]
+    off = np.concatenate([[0], np.cumsum(ns)]).astype(np.int32)
+    imgs = np.stack([so.votes_to_image(so.sphere_votes(l, 250)) for l in lines])
+    resp = np.stack([synth.ideal_response(s["vps"], seed=i) for i, s in enumerate(scs)])
+    out = em.expectation_maximisation_batch(np.concatenate(lines), np.concatenate(segs), off, resp, imgs)
+    again = em.expectation_maximisation_batch(np.concatenate(lines), np.concatenate(segs), off, resp, imgs)
+    n_vp = 0
+    for b in range(len(ns)):
+        single = em.expectation_maximisation(lines[b].copy(), segs[b].copy(), resp[b], sphere_image=imgs[b])
+        assert (out[b]["vp"] is None) == (single["vp"] is None)
+        if single["vp"] is None:
+            continue
+        n_vp += 1
+        for res in (out[b], again[b]):
+            np.testing.assert_array_equal(res["vp"], single["vp"])
+            np.testing.assert_array_equal(res["vp_assoc"], single["vp_assoc"])
+            np.testing.assert_array_equal(res["counts"], single["counts"])
+            assert res["iterations"] == single["iterations"]
+    assert n_vp >= 60
+
+
 def test_kwargs_and_errors(em):
     sc = synth.make_scene(31, 200)
     img = so.votes_to_image(so.sphere_votes(sc["lines"], 250))

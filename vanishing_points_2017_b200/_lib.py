@@ -73,7 +73,7 @@ def load():
         lib.vpk_cnn_load.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.vpk_cnn_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         lib.vpk_debug_gemm.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
-                                       C.c_int32, C.c_int32, C.c_void_p]
+                                       C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
         lib.vpk_em_default_config.argtypes = [C.POINTER(EmConfig)]
         lib.vpk_em_default_config.restype = None
         lib.vpk_em.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,

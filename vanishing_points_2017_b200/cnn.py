@@ -100,7 +100,7 @@ def caffe_forward(net, image, mean_arr):
     return net.forward_batch(image[None])[0]
 
 
-def debug_gemm(a_bf16_bits, b_bf16_bits, bias=None, relu=False, bn=128, ctx=None):
+def debug_gemm(a_bf16_bits, b_bf16_bits, bias=None, relu=False, bn=128, ksplit=1, ctx=None):
     ctx = ctx or _lib.default_context()
     a = np.ascontiguousarray(a_bf16_bits, dtype=np.uint16)
     b = np.ascontiguousarray(b_bf16_bits, dtype=np.uint16)
@@ -109,5 +109,5 @@ def debug_gemm(a_bf16_bits, b_bf16_bits, bias=None, relu=False, bn=128, ctx=None
     out = np.empty((m, n), dtype=np.float32)
     bias = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
     _lib.check(ctx.lib.vpk_debug_gemm(ctx.h, m, n, k, _lib.ptr(a), _lib.ptr(b), _lib.ptr(bias), int(relu), int(bn),
-                                      _lib.ptr(out)), "vpk_debug_gemm")
+                                      int(ksplit), _lib.ptr(out)), "vpk_debug_gemm")
     return out

@@ -507,8 +507,8 @@ int vpk_cnn_forward(vpk_ctx* ctx, const uint8_t* images, int32_t n, float* sigou
 // Diagnostics: one plain GEMM through the tcgen05 kernel.  a (m,k), b (n,k) are
 // bf16 bit patterns (uint16), bias (n) float32 or NULL, out (m,n) float32.
 int vpk_debug_gemm(vpk_ctx* ctx, int32_t m, int32_t n, int32_t k, const uint16_t* a, const uint16_t* b, const float* bias,
-                   int32_t relu, int32_t bn, float* out) {
-    if (!ctx || !a || !b || !out || m <= 0 || n <= 0 || k <= 0 || k % 64 || bn % 16 || bn < 16 || bn > 256 || n % bn) {
+                   int32_t relu, int32_t bn, int32_t ksplit, float* out) {
+    if (!ctx || !a || !b || !out || m <= 0 || n <= 0 || k <= 0 || k % 64 || bn % 16 || bn < 16 || bn > 256 || n % bn || ksplit < 1) {
         set_error("vpk_debug_gemm: bad argument (k %% 64 == 0, bn %% 16 == 0, n %% bn == 0 required)");
         return VPK_ERR_ARG;
     }
@@ -528,7 +528,7 @@ int vpk_debug_gemm(vpk_ctx* ctx, int32_t m, int32_t n, int32_t k, const uint16_t
         c.name = "gemm_debug"; c.A = da.p; c.a_inner = k; c.a_rows = m; c.a_pitch = (uint64_t)k * 2;
         c.B = db.p; c.b_inner = k; c.b_rows = n; c.groups = 1;
         c.p = plain_params(m, n, k, bn, n, bias ? dbias.as<float>() : nullptr, relu, 1, dout.p);
-        if ((rc = launch_gemm(ctx, c))) break;
+        if ((rc = launch_gemm_splitk(ctx, c, ksplit, "splitk_debug"))) break;
         cudaMemcpyAsync(out, dout.p, (size_t)m * n * 4, cudaMemcpyDeviceToHost, ctx->stream);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { set_error("vpk_debug_gemm: %s", cudaGetErrorString(e)); rc = VPK_ERR_CUDA; }

@@ -27,6 +27,7 @@
 // decisions (counts < 3, argmax, err > 1.5, angle < thresh) sit on float values
 // and the parity gate is 1e-4 rad on the refined VPs.
 #include <algorithm>
+#include <vector>
 #include <chrono>
 #include <cstdio>
 #include "em_core.cuh"
@@ -617,7 +618,21 @@ struct EmLoopGraph {
 constexpr int kMaxGroups = 8;
 constexpr int kGroupSlots = 26;       // images per group (default; VPK_EM_GROUPS overrides the group count)
 
+struct GroupRun { EmParams P; cudaStream_t s; int n, nmax, csl, bound, step; bool done; };
+struct EmWave {
+    bool begun = false;                    // wave_begin done, wave_run pending
+    bool device_loop = true;
+    int begin = 0, end = 0, n = 0, G = 0;
+    size_t budget = 0;
+    std::vector<int32_t> order;
+    EmParams P, key_P;
+    GroupRun R[kMaxGroups];
+    int key_B = 0;
+    const int32_t* key_off = nullptr;
+};
+
 struct EmState {
+    EmWave wave;
     DBuf ws, slots, desc, lists, alive, ctl, stats, overflow, resp, out_small, out_assoc, out_dm, init_vp, init_off, sphere;
     HBuf h_desc, h_cnt;
     bool attr_set = false;
@@ -625,7 +640,7 @@ struct EmState {
     cudaStream_t gstream[kMaxGroups] = {};
     cudaEvent_t gdone[kMaxGroups] = {};
     cudaEvent_t gev[kMaxGroups][8] = {};
-    cudaEvent_t fork = nullptr;
+    cudaEvent_t fork = nullptr, ready = nullptr;
     int last_supersteps = 0;
     unsigned long long totals[6] = {0, 0, 0, 0, 0, 0};   // accumulated W-product statistics + supersteps (profiling runs)
 };
@@ -641,6 +656,7 @@ void em_free(vpk_ctx* ctx) {
     for (auto& g : e->gdone) if (g) cudaEventDestroy(g);
     for (auto& r : e->gev) for (auto& g : r) if (g) cudaEventDestroy(g);
     if (e->fork) cudaEventDestroy(e->fork);
+    if (e->ready) cudaEventDestroy(e->ready);
     delete e;
     ctx->em = nullptr;
 }
@@ -720,62 +736,135 @@ static int build_loop_graph(vpk_ctx* ctx, cudaStream_t sm, EmLoopGraph& G, const
     return VPK_OK;
 }
 
-// one wave: slots [0, n) described by h_desc (already in pinned memory); group g = slots [gstart[g], gstart[g+1])
-// with at most gnmax[g] segments each.  Every group runs its supersteps on its own stream, driven either
-// by a device-side loop graph (the default) or by the host (VPK_EM_HOST_LOOP=1 and profiling runs:
-// supersteps enqueued in chunks, the active count read LA chunks behind).
-static int em_wave(vpk_ctx* ctx, EmState* st, EmParams& P, int n, int G, const int* gstart, const int* gnmax, bool device_loop) {
-    cudaStream_t sm = ctx->stream;
-    VPK_CUDA(cudaMemcpyAsync(st->desc.p, st->h_desc.p, sizeof(SlotDesc) * (size_t)n, cudaMemcpyHostToDevice, sm));
-    VPK_CUDA(cudaMemsetAsync(st->ctl.p, 0, (kMaxGroups + 1) * kCtlInts * sizeof(int), sm));
-    if (P.stats) VPK_CUDA(cudaMemsetAsync(P.stats, 0, 32 * sizeof(unsigned long long), sm));
-    const int max_steps = 64 * (P.cfg.num_iter + 8);
-    int* h_cnt = st->h_cnt.as<int>();
-    static const bool trace = getenv("VPK_EM_TRACE") != nullptr;
-    const auto t_begin = std::chrono::steady_clock::now();
-    int rebuilt = 0;
-    if (G > 1) VPK_CUDA(cudaEventRecord(st->fork, sm));
+// ---- one wave = the images (heaviest first) that fit the workspace.  Group g = slots
+// [gstart[g], gstart[g+1]) runs its supersteps on its own stream, driven by a device-side loop graph
+// (the default) or by the host (VPK_EM_HOST_LOOP=1 and profiling runs: supersteps enqueued in chunks,
+// the active count read LA chunks behind).  wave_begin needs the segments only (slot layout, pair
+// pass); wave_run needs the CNN response and the sphere images (initial hypotheses, supersteps).
 
-    struct GroupRun { EmParams P; cudaStream_t s; int n, nmax, csl, bound, step; bool done; };
-    GroupRun R[kMaxGroups];
+// plan of wave [begin, end) of `order`: buffers, slot descriptors, groups, kernel parameters
+static int plan_wave(vpk_ctx* ctx, EmState* st, const EmParams& P0, const int32_t* h_offsets, int B) {
+    EmWave& W = st->wave;
+    const int begin = W.begin;
+    size_t doubles = 0;
+    int end = begin;
+    const int nmax = std::max(1, h_offsets[W.order[begin] + 1] - h_offsets[W.order[begin]]);
+    while (end < B && end - begin < 32768) {
+        const int N = h_offsets[W.order[end] + 1] - h_offsets[W.order[end]];
+        const size_t need = slot_doubles(N);
+        if (end > begin && doubles + need > W.budget) break;
+        doubles += need;
+        ++end;
+    }
+    const int n = end - begin;
+    VPK_TRY(st->ws.ensure(doubles * sizeof(double)));
+    VPK_TRY(st->slots.ensure(sizeof(EmSlot) * (size_t)n));
+    VPK_TRY(st->desc.ensure(sizeof(SlotDesc) * (size_t)n));
+    VPK_TRY(st->lists.ensure(2 * sizeof(int) * (size_t)n));
+    VPK_TRY(st->alive.ensure(sizeof(int) * (size_t)n));
+    const size_t ov = (size_t)nmax * nmax + 6 * (size_t)nmax + 16;
+    VPK_TRY(st->overflow.ensure(ov * sizeof(double)));
+    VPK_TRY(st->h_desc.ensure(sizeof(SlotDesc) * (size_t)n));
+    SlotDesc* hd = st->h_desc.as<SlotDesc>();
+    // groups: the wave's images (heaviest first) are dealt round-robin, so every group gets the same
+    // mix of sizes; a group's slots are contiguous.  One group per ~kGroupSlots images.
+    static const int env_groups = getenv("VPK_EM_GROUPS") ? atoi(getenv("VPK_EM_GROUPS")) : 0;
+    static const bool host_loop_env = getenv("VPK_EM_HOST_LOOP") != nullptr;
+    W.device_loop = !host_loop_env && !ctx->profiling;   // no per-kernel events inside a graph
+    int G = env_groups > 0 ? env_groups : (n + kGroupSlots - 1) / kGroupSlots;
+    G = std::max(1, std::min(G, std::min(n, kMaxGroups)));
+    if (ctx->profiling) G = 1;          // per-kernel events are recorded on the context's stream
+    EmParams P;
+    memcpy(&P, &P0, sizeof(EmParams));
+    P.slots = st->slots.as<EmSlot>(); P.desc = st->desc.as<SlotDesc>(); P.ws = st->ws.as<double>();
+    P.lists = st->lists.as<int>(); P.alive = st->alive.as<int>(); P.ctl = st->ctl.as<int>();
+    P.ovlock = st->ctl.as<int>() + kMaxGroups * kCtlInts;
+    P.stats = ctx->profiling ? st->stats.as<unsigned long long>() : nullptr;
+    P.overflow = st->overflow.as<double>(); P.overflow_cap = ov;
+    P.n_slots = n;
+    size_t off = 0;
+    int i = 0;
     for (int g = 0; g < G; ++g) {
-        GroupRun& r = R[g];
-        r.s = G > 1 ? st->gstream[g] : sm;
-        if (G > 1) VPK_CUDA(cudaStreamWaitEvent(r.s, st->fork, 0));
+        GroupRun& r = W.R[g];
+        const int g0 = i;
+        r.nmax = 1;
+        for (int k = g; k < n; k += G, ++i) {
+            const int b = W.order[begin + k];
+            hd[i].img = b; hd[i].base = h_offsets[b]; hd[i].N = h_offsets[b + 1] - h_offsets[b]; hd[i].pad = 0;
+            hd[i].ws_off = off;
+            off += slot_doubles(hd[i].N);
+            r.nmax = std::max(r.nmax, hd[i].N);
+        }
+        r.s = ctx->profiling ? ctx->stream : st->gstream[g];
         memcpy(&r.P, &P, sizeof(EmParams));      // padding included: the loop graph is keyed on the bytes
-        const int g0 = gstart[g];
-        r.n = gstart[g + 1] - g0; r.nmax = gnmax[g]; r.csl = wmat_split(r.nmax); r.bound = r.n; r.step = 0; r.done = false;
+        r.n = i - g0; r.csl = wmat_split(r.nmax); r.bound = r.n; r.step = 0; r.done = false;
         r.P.slots = P.slots + g0; r.P.desc = P.desc + g0; r.P.lists = P.lists + 2 * (size_t)g0; r.P.alive = P.alive + g0;
         r.P.ctl = P.ctl + g * kCtlInts; r.P.n_slots = r.n;
+    }
+    memcpy(&W.P, &P, sizeof(EmParams));
+    W.n = n; W.G = G; W.end = end;
+    return VPK_OK;
+}
+
+// descriptors, control words, pair pass (E3 + E4) of every group on its stream
+static int wave_begin(vpk_ctx* ctx, EmState* st) {
+    EmWave& W = st->wave;
+    cudaStream_t sm = ctx->stream;
+    VPK_CUDA(cudaMemcpyAsync(st->desc.p, st->h_desc.p, sizeof(SlotDesc) * (size_t)W.n, cudaMemcpyHostToDevice, sm));
+    VPK_CUDA(cudaMemsetAsync(st->ctl.p, 0, (kMaxGroups + 1) * kCtlInts * sizeof(int), sm));
+    if (W.P.stats) VPK_CUDA(cudaMemsetAsync(W.P.stats, 0, 32 * sizeof(unsigned long long), sm));
+    VPK_CUDA(cudaEventRecord(st->fork, sm));
+    for (int g = 0; g < W.G; ++g) {
+        GroupRun& r = W.R[g];
+        if (r.s != sm) VPK_CUDA(cudaStreamWaitEvent(r.s, st->fork, 0));
         if (r.P.cfg.use_weights) {
             KernelScope ks(ctx, "em_pair");
             em_pair_kernel<<<dim3((r.nmax + kTK - 1) / kTK, r.n), kPairThreads, 0, r.s>>>(r.P);
             VPK_TRY(check_launch("em_pair"));
         }
+    }
+    W.begun = true;
+    return VPK_OK;
+}
+
+// initial hypotheses and the superstep loops; returns when every slot of the wave is finished
+static int wave_run(vpk_ctx* ctx, EmState* st) {
+    EmWave& W = st->wave;
+    cudaStream_t sm = ctx->stream;
+    const int G = W.G;
+    const int max_steps = 64 * (W.P.cfg.num_iter + 8);
+    int* h_cnt = st->h_cnt.as<int>();
+    static const bool trace = getenv("VPK_EM_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    int rebuilt = 0;
+    W.begun = false;
+    VPK_CUDA(cudaEventRecord(st->ready, sm));          // CNN response and sphere images are complete
+    auto join = [&](int g) {
+        if (W.R[g].s == sm) return cudaSuccess;
+        cudaError_t e = cudaEventRecord(st->gdone[g], W.R[g].s);
+        return e != cudaSuccess ? e : cudaStreamWaitEvent(sm, st->gdone[g], 0);
+    };
+    for (int g = 0; g < G; ++g) {
+        GroupRun& r = W.R[g];
+        if (r.s != sm) VPK_CUDA(cudaStreamWaitEvent(r.s, st->ready, 0));
         {
             KernelScope ks(ctx, "em_init");
             em_init_kernel<<<r.n, kInitThreads, 0, r.s>>>(r.P);
             VPK_TRY(check_launch("em_init"));
         }
-        if (device_loop) {
+        if (W.device_loop) {
             EmLoopGraph& L = *st->loop[g];
             if (!L.exec || L.n != r.n || L.nmax != r.nmax || memcmp(&L.key, &r.P, sizeof(EmParams)) != 0) {
                 VPK_TRY(build_loop_graph(ctx, r.s, L, r.P, r.n, r.nmax, max_steps));
                 ++rebuilt;
             }
             VPK_CUDA(cudaGraphLaunch(L.exec, r.s));
+            VPK_CUDA(join(g));
         }
     }
     int steps = 0;
-    if (device_loop) {
-        for (int g = 0; g < G && G > 1; ++g) {
-            VPK_CUDA(cudaEventRecord(st->gdone[g], R[g].s));
-            VPK_CUDA(cudaStreamWaitEvent(sm, st->gdone[g], 0));
-        }
-        VPK_CUDA(cudaMemcpyAsync(h_cnt, P.ctl, G * kCtlInts * sizeof(int), cudaMemcpyDeviceToHost, sm));
-        if (trace)
-            fprintf(stderr, "[vpk_em] enqueue %.3f ms\n",
-                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    if (W.device_loop) {
+        VPK_CUDA(cudaMemcpyAsync(h_cnt, W.P.ctl, G * kCtlInts * sizeof(int), cudaMemcpyDeviceToHost, sm));
         VPK_CUDA(cudaStreamSynchronize(sm));
         for (int g = 0; g < G; ++g) {
             const int* c = h_cnt + g * kCtlInts;
@@ -791,7 +880,7 @@ static int em_wave(vpk_ctx* ctx, EmState* st, EmParams& P, int n, int G, const i
         int active = G;
         for (int chunk = 0; active > 0; ++chunk) {
             for (int g = 0; g < G; ++g) {
-                GroupRun& r = R[g];
+                GroupRun& r = W.R[g];
                 if (r.done) continue;
                 int* ring = h_cnt + g * 8;
                 if (chunk >= LA) {
@@ -800,10 +889,7 @@ static int em_wave(vpk_ctx* ctx, EmState* st, EmParams& P, int n, int G, const i
                     if (r.bound <= 0) {
                         r.done = true;
                         --active;
-                        if (G > 1) {
-                            VPK_CUDA(cudaEventRecord(st->gdone[g], r.s));
-                            VPK_CUDA(cudaStreamWaitEvent(sm, st->gdone[g], 0));
-                        }
+                        VPK_CUDA(join(g));
                         continue;
                     }
                 }
@@ -816,24 +902,24 @@ static int em_wave(vpk_ctx* ctx, EmState* st, EmParams& P, int n, int G, const i
             }
         }
         VPK_CUDA(cudaStreamSynchronize(sm));
-        for (int g = 0; g < G; ++g) steps = std::max(steps, R[g].step);
+        for (int g = 0; g < G; ++g) steps = std::max(steps, W.R[g].step);
     }
     if (trace) {
         const auto t_end = std::chrono::steady_clock::now();
-        fprintf(stderr, "[vpk_em] wave n=%d groups=%d %s loop, graphs rebuilt=%d, supersteps %d, %.3f ms\n", n, G,
-                device_loop ? "device" : "host", rebuilt, steps, std::chrono::duration<double, std::milli>(t_end - t_begin).count());
+        fprintf(stderr, "[vpk_em] wave n=%d groups=%d %s loop, graphs rebuilt=%d, supersteps %d, %.3f ms\n", W.n, G,
+                W.device_loop ? "device" : "host", rebuilt, steps, std::chrono::duration<double, std::milli>(t_end - t_begin).count());
     }
     st->last_supersteps = steps;
-    if (P.stats) {
+    if (W.P.stats) {
         unsigned long long h[5] = {0, 0, 0, 0, 0};
-        VPK_CUDA(cudaMemcpy(h, P.stats, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        VPK_CUDA(cudaMemcpy(h, W.P.stats, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         for (int k = 0; k < 3; ++k) st->totals[k] += h[k];
         st->totals[3] += (unsigned long long)steps;
         st->totals[4] += h[3];
         st->totals[5] += h[4];
 #if defined(VPK_EM_MARKS)
         unsigned long long mk[11];
-        VPK_CUDA(cudaMemcpy(mk, P.stats + 8, 11 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        VPK_CUDA(cudaMemcpy(mk, W.P.stats + 8, 11 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         fprintf(stderr, "[vpk_em] POST cycles per slot-superstep (%llu):", mk[10]);
         for (int k = 0; k < 10; ++k) fprintf(stderr, " m%d=%.0f", k, (double)mk[k] / (double)std::max<unsigned long long>(mk[10], 1));
         fprintf(stderr, "\n");
@@ -842,10 +928,13 @@ static int em_wave(vpk_ctx* ctx, EmState* st, EmParams& P, int n, int G, const i
     return VPK_OK;
 }
 
+// phase EM_ALL: the whole stage.  EM_EARLY: only what needs the segments (layout and pair pass of the
+// first wave, on the group streams: overlaps whatever the caller enqueues on the context's stream
+// afterwards, i.e. sphere mapping and the CNN); the matching EM_ALL call then continues from there.
 int em_dev(vpk_ctx* ctx, const double* d_lines, const double* d_segments, const int32_t* d_offsets,
            const int32_t* h_offsets, int32_t B, const float* d_resp_f32, const double* d_resp_f64,
            const uint8_t* d_sphere, int32_t S, const double* d_init_vp, const int32_t* d_init_off,
-           const vpk_em_config* cfg, const EmDeviceOut& out) {
+           const vpk_em_config* cfg, const EmDeviceOut& out, int phase) {
     (void)d_offsets;
     if (B <= 0) return VPK_OK;
     if (!ctx->em) ctx->em = new EmState();
@@ -856,31 +945,12 @@ int em_dev(vpk_ctx* ctx, const double* d_lines, const double* d_segments, const 
         for (auto& ev : st->gdone) VPK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& r : st->gev) for (auto& ev : r) VPK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         VPK_CUDA(cudaEventCreateWithFlags(&st->fork, cudaEventDisableTiming));
+        VPK_CUDA(cudaEventCreateWithFlags(&st->ready, cudaEventDisableTiming));
         for (auto& g : st->gstream) VPK_CUDA(cudaStreamCreateWithFlags(&g, cudaStreamNonBlocking));
         for (auto& l : st->loop) l = new EmLoopGraph();
         st->attr_set = true;
     }
-    // heaviest images first
-    std::vector<int32_t> order(B);
-    for (int b = 0; b < B; ++b) order[b] = b;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-        return (h_offsets[a + 1] - h_offsets[a]) > (h_offsets[b + 1] - h_offsets[b]);
-    });
-    // workspace budget of a wave: the whole batch if the workspace already holds it (no driver query on
-    // the steady-state path), else half of what is free
-    size_t all_doubles = 0;
-    for (int b = 0; b < B; ++b) all_doubles += slot_doubles(h_offsets[b + 1] - h_offsets[b]);
-    size_t budget = all_doubles;
-    if (all_doubles * sizeof(double) > st->ws.cap) {
-        size_t free_b = 0, total_b = 0;
-        VPK_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        budget = std::max<size_t>((free_b + st->ws.cap) / 2, (size_t)1 << 28) / sizeof(double);
-    }
-    static const bool trace_dev = getenv("VPK_EM_TRACE") != nullptr;
-    const auto t_dev0 = std::chrono::steady_clock::now();
-    VPK_TRY(st->h_cnt.ensure(kMaxGroups * 8 * sizeof(int)));
-    VPK_TRY(st->ctl.ensure((kMaxGroups + 1) * kCtlInts * sizeof(int)));
-    VPK_TRY(st->stats.ensure(32 * sizeof(unsigned long long)));
+    EmWave& W = st->wave;
 
     EmParams P;
     memset(&P, 0, sizeof(P));                   // padding included: the loop graph is keyed on the bytes
@@ -892,62 +962,45 @@ int em_dev(vpk_ctx* ctx, const double* d_lines, const double* d_segments, const 
     P.out.sigma = out.sigma; P.out.counts = out.counts; P.out.counts_weighted = out.counts_weighted;
     P.out.vp_assoc = out.vp_assoc; P.out.decision_metric = out.decision_metric;
 
-    int begin = 0;
-    while (begin < B) {
-        // a wave: as many images (in order) as fit the workspace budget
-        size_t doubles = 0;
-        int end = begin;
-        const int nmax = std::max(1, h_offsets[order[begin] + 1] - h_offsets[order[begin]]);
-        while (end < B && end - begin < 32768) {
-            const int N = h_offsets[order[end] + 1] - h_offsets[order[end]];
-            const size_t need = slot_doubles(N);
-            if (end > begin && doubles + need > budget) break;
-            doubles += need;
-            ++end;
+    // continue a wave begun by an EM_EARLY call with the same arguments?
+    const bool resume = W.begun && phase == EM_ALL && W.key_B == B && W.key_off == h_offsets && memcmp(&W.key_P, &P, sizeof(EmParams)) == 0;
+    if (W.begun && !resume) {
+        // an early pair pass nobody continued: drain it before its buffers are reused
+        for (int g = 0; g < W.G; ++g) VPK_CUDA(cudaStreamSynchronize(W.R[g].s));
+        W.begun = false;
+    }
+    if (!resume) {
+        // heaviest images first
+        W.order.resize(B);
+        for (int b = 0; b < B; ++b) W.order[b] = b;
+        std::stable_sort(W.order.begin(), W.order.end(), [&](int a, int b) {
+            return (h_offsets[a + 1] - h_offsets[a]) > (h_offsets[b + 1] - h_offsets[b]);
+        });
+        // workspace budget of a wave: the whole batch if the workspace already holds it (no driver query on
+        // the steady-state path), else half of what is free
+        size_t all_doubles = 0;
+        for (int b = 0; b < B; ++b) all_doubles += slot_doubles(h_offsets[b + 1] - h_offsets[b]);
+        W.budget = all_doubles;
+        if (all_doubles * sizeof(double) > st->ws.cap) {
+            size_t free_b = 0, total_b = 0;
+            VPK_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            W.budget = std::max<size_t>((free_b + st->ws.cap) / 2, (size_t)1 << 28) / sizeof(double);
         }
-        const int n = end - begin;
-        VPK_TRY(st->ws.ensure(doubles * sizeof(double)));
-        VPK_TRY(st->slots.ensure(sizeof(EmSlot) * (size_t)n));
-        VPK_TRY(st->desc.ensure(sizeof(SlotDesc) * (size_t)n));
-        VPK_TRY(st->lists.ensure(2 * sizeof(int) * (size_t)n));
-        VPK_TRY(st->alive.ensure(sizeof(int) * (size_t)n));
-        const size_t ov = (size_t)nmax * nmax + 6 * (size_t)nmax + 16;
-        VPK_TRY(st->overflow.ensure(ov * sizeof(double)));
-        VPK_TRY(st->h_desc.ensure(sizeof(SlotDesc) * (size_t)n));
-        SlotDesc* hd = st->h_desc.as<SlotDesc>();
-        // groups: the wave's images (heaviest first) are dealt round-robin, so every group gets the same
-        // mix of sizes; a group's slots are contiguous.  One group per ~kGroupSlots images.
-        static const int env_groups = getenv("VPK_EM_GROUPS") ? atoi(getenv("VPK_EM_GROUPS")) : 0;
-        static const bool host_loop_env = getenv("VPK_EM_HOST_LOOP") != nullptr;
-        const bool device_loop = !host_loop_env && !ctx->profiling;   // no per-kernel events inside a graph
-        int G = env_groups > 0 ? env_groups : (n + kGroupSlots - 1) / kGroupSlots;
-        G = std::max(1, std::min(G, std::min(n, kMaxGroups)));
-        if (ctx->profiling) G = 1;          // per-kernel events are recorded on the context's stream
-        int gstart[kMaxGroups + 1], gnmax[kMaxGroups];
-        size_t off = 0;
-        int i = 0;
-        for (int g = 0; g < G; ++g) {
-            gstart[g] = i;
-            gnmax[g] = 1;
-            for (int k = g; k < n; k += G, ++i) {
-                const int b = order[begin + k];
-                hd[i].img = b; hd[i].base = h_offsets[b]; hd[i].N = h_offsets[b + 1] - h_offsets[b]; hd[i].pad = 0;
-                hd[i].ws_off = off;
-                off += slot_doubles(hd[i].N);
-                gnmax[g] = std::max(gnmax[g], hd[i].N);
-            }
+        VPK_TRY(st->h_cnt.ensure(kMaxGroups * 8 * sizeof(int)));
+        VPK_TRY(st->ctl.ensure((kMaxGroups + 1) * kCtlInts * sizeof(int)));
+        VPK_TRY(st->stats.ensure(32 * sizeof(unsigned long long)));
+        W.begin = 0;
+        W.key_B = B; W.key_off = h_offsets;
+        memcpy(&W.key_P, &P, sizeof(EmParams));
+    }
+    while (W.begin < B) {
+        if (!W.begun) {
+            VPK_TRY(plan_wave(ctx, st, P, h_offsets, B));
+            VPK_TRY(wave_begin(ctx, st));
         }
-        gstart[G] = n;
-        P.slots = st->slots.as<EmSlot>(); P.desc = st->desc.as<SlotDesc>(); P.ws = st->ws.as<double>();
-        P.lists = st->lists.as<int>(); P.alive = st->alive.as<int>(); P.ctl = st->ctl.as<int>();
-        P.ovlock = st->ctl.as<int>() + kMaxGroups * kCtlInts;
-        P.stats = ctx->profiling ? st->stats.as<unsigned long long>() : nullptr;
-        P.overflow = st->overflow.as<double>(); P.overflow_cap = ov;
-        if (trace_dev)
-            fprintf(stderr, "[vpk_em] host set-up %.3f ms\n",
-                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_dev0).count());
-        VPK_TRY(em_wave(ctx, st, P, n, G, gstart, gnmax, device_loop));
-        begin = end;
+        if (phase == EM_EARLY) return VPK_OK;
+        VPK_TRY(wave_run(ctx, st));
+        W.begin = W.end;
     }
     return VPK_OK;
 }

@@ -78,6 +78,23 @@ int vpk_pipeline_run(vpk_ctx* ctx, int32_t S, int32_t sphere_mode, double alpha,
     p->S = S;
     VPK_CUDA(cudaEventRecord(p->ev[0], ctx->stream));
     VPK_TRY(lines_from_segments_dev(ctx, p->seg.as<double>(), p->sumN, p->lines.as<double>()));
+    // stage 3, early part: the segment-pair pass of the EM (similarity matrices, line ratings) needs the
+    // segments only; it runs on the EM's own streams underneath stages 1 and 2
+    EmDeviceOut d;
+    double* f = p->out_small.as<double>();
+    d.vp = f; f += (size_t)B * VPK_MAX_VP * 3;
+    d.sigma = f; f += (size_t)B * VPK_MAX_VP;
+    d.counts_weighted = f; f += (size_t)B * VPK_MAX_VP;
+    int32_t* ip = reinterpret_cast<int32_t*>(f);
+    d.status = ip; ip += B;
+    d.n_vp = ip; ip += B;
+    d.iterations = ip; ip += B;
+    d.counts = ip;
+    d.vp_assoc = p->out_assoc.as<int32_t>();
+    d.decision_metric = nullptr;
+    p->out = d;
+    VPK_TRY(em_dev(ctx, p->lines.as<double>(), p->seg.as<double>(), p->offsets.as<int32_t>(), p->h_offsets.data(), B,
+                   p->sigout.as<float>(), nullptr, p->images.as<uint8_t>(), S, nullptr, nullptr, &cfg, d, EM_EARLY));
     // stage 1 for the whole batch, chunked
     for (int c0 = 0; c0 < B; c0 += chunk) {
         const int nb = B - c0 < chunk ? B - c0 : chunk;
@@ -94,20 +111,7 @@ int vpk_pipeline_run(vpk_ctx* ctx, int32_t S, int32_t sphere_mode, double alpha,
         VPK_TRY(cnn_forward_dev(ctx, p->images.as<uint8_t>() + plane * c0, nb, p->sigout.as<float>() + (size_t)kCells * c0, nullptr));
     }
     VPK_CUDA(cudaEventRecord(p->ev[2], ctx->stream));
-    // stage 3
-    EmDeviceOut d;
-    double* f = p->out_small.as<double>();
-    d.vp = f; f += (size_t)B * VPK_MAX_VP * 3;
-    d.sigma = f; f += (size_t)B * VPK_MAX_VP;
-    d.counts_weighted = f; f += (size_t)B * VPK_MAX_VP;
-    int32_t* ip = reinterpret_cast<int32_t*>(f);
-    d.status = ip; ip += B;
-    d.n_vp = ip; ip += B;
-    d.iterations = ip; ip += B;
-    d.counts = ip;
-    d.vp_assoc = p->out_assoc.as<int32_t>();
-    d.decision_metric = nullptr;
-    p->out = d;
+    // stage 3 (the rest: initial hypotheses and the supersteps)
     VPK_TRY(em_dev(ctx, p->lines.as<double>(), p->seg.as<double>(), p->offsets.as<int32_t>(), p->h_offsets.data(), B,
                    p->sigout.as<float>(), nullptr, p->images.as<uint8_t>(), S, nullptr, nullptr, &cfg, d));
     VPK_CUDA(cudaEventRecord(p->ev[3], ctx->stream));

@@ -178,7 +178,8 @@ struct EmDeviceOut {
 int em_dev(vpk_ctx* ctx, const double* d_lines, const double* d_segments, const int32_t* d_offsets,
            const int32_t* h_offsets, int32_t B, const float* d_resp_f32, const double* d_resp_f64,
            const uint8_t* d_sphere, int32_t S, const double* d_init_vp, const int32_t* d_init_off,
-           const vpk_em_config* cfg, const EmDeviceOut& out);
+           const vpk_em_config* cfg, const EmDeviceOut& out, int phase = 0);
+enum { EM_ALL = 0, EM_EARLY = 1 };
 
 void cnn_free(vpk_ctx* ctx);
 void em_free(vpk_ctx* ctx);
