@@ -20,8 +20,10 @@
 //               em_post  (CTA = image: reductions over the lines, 3x3
 //                         eigen-solves, prune / split / merge / convergence
 //                         decisions E7-E12, choice of the next superstep).
-//   The host enqueues supersteps in chunks and reads the number of still-active
-//   slots two chunks behind, so the device never waits for the host.
+//   The images of a wave are dealt to groups; every group runs its supersteps on its own
+//   stream, driven by a device-side loop (CUDA graph of conditional WHILE nodes) or, for
+//   profiling, by the host (chunks of supersteps, the active count read three chunks behind),
+//   so that the latency-bound POST of one group overlaps the HBM-bound W of the others.
 //
 // Arithmetic is float64 throughout: the reference is float64, its discrete
 // decisions (counts < 3, argmax, err > 1.5, angle < thresh) sit on float values
