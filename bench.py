@@ -7,7 +7,7 @@ One "step" = one pass of the path (segments -> lines -> sphere votes -> CNN ->
 EM -> VPs) over one synthetic batch of BASELINE.json config C (default 2: the
 YUD-shaped batch, 102 images 640x480, ~500 segments, single B200).  With N > 1
 (launched by torch.distributed.run, one rank per GPU) every rank runs its own
-batch of the same shape: images are independent, so there is no data-path
+copy of the same batch (fixed per-GPU work): images are independent, so there is no data-path
 collective (weak scaling); the only exchange is the timing reduction.
 
 value    : whole-job images/s with the batch already resident in HBM (device
@@ -216,7 +216,8 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     peaks = load_peaks()
-    name, seg, off = make_workload(args.config, rank, args.images)
+    # weak scaling with FIXED per-GPU work: every rank processes the same synthetic batch
+    name, seg, off = make_workload(args.config, 0, args.images)
     B = len(off) - 1
     ws, bs = vcnn.random_weights(0, scale=args.weight_scale)
     pipe = pipeline.Pipeline(local_rank, ws, bs, sphere_mode=args.sphere_mode)
@@ -384,7 +385,8 @@ def run_ours(args, rank, world, local_rank):
                        "images_per_gpu": B, "segments_per_image_mean": float(np.mean(np.diff(off))),
                        "sphere_size": 500, "sphere_mode": args.sphere_mode, "cnn_weights": "random-init "
                        "(train_val.prototxt fillers x%g, seed 0)" % args.weight_scale,
-                       "l2": "flushed between steps (256 MiB memset)", "parallelism": "images sharded, no collective"},
+                       "l2": "flushed between steps (256 MiB memset)",
+                       "parallelism": "images sharded, no collective; every rank runs the same batch (fixed per-GPU work)"},
             "e2e": {"value": total_images / (e2e_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_step},
             "gpu_launches": int(launches),
