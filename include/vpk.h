@@ -173,6 +173,21 @@ VPK_API int vpk_pipeline_fetch(vpk_ctx* ctx, vpk_em_result* out, float* sigout /
 VPK_API int vpk_pipeline_host(vpk_ctx* ctx, const double* segments, const int32_t* offsets, int32_t n_images,
                       int32_t size, int32_t sphere_mode, double alpha, const vpk_em_config* cfg,
                       vpk_em_result* out, float* sigout, uint8_t* sphere_images);
+/* ---- N1: horizon line and orthogonal VP triplet --------------------------- */
+/* calc_horizon.calculate_horizon_and_ortho_vp(em_result, maxbest=10, theta_vmin=pi/10, theta_z=pi/4)
+ * (reference calc_horizon.py:19-225; callers example.py:65, benchmark.py:233) for a batch of EM
+ * results.  vp (B, VPK_MAX_VP, 3) float64, counts (B, VPK_MAX_VP) int32 and n_vp (B) int32 are laid
+ * out as vpk_em writes them (an image without VPs has n_vp = 0 and gets the reference's default
+ * horizon, calc_horizon.py:207-212).  points (B, 5, 3) float64 receives the reference's return
+ * values hP1, hP2, zVP, hVP1, hVP2 in that order; best_combo (B, 3) int32 the indices of the chosen
+ * VPs (two entries and -1 when fewer than three VPs take part). */
+VPK_API int vpk_horizon(vpk_ctx* ctx, const double* vp, const int32_t* counts, const int32_t* n_vp, int32_t n_images,
+                        int32_t maxbest, double theta_vmin, double theta_z, double* points, int32_t* best_combo);
+/* The same on the device-resident EM result of the last vpk_pipeline_run (no host round trip of the
+ * EM result; only the 5 points + 3 indices per image come back). */
+VPK_API int vpk_pipeline_horizon(vpk_ctx* ctx, int32_t maxbest, double theta_vmin, double theta_z, double* points,
+                                 int32_t* best_combo);
+
 /* device time of the last vpk_pipeline_run per stage: [lines+sphere, cnn, em, total] ms */
 VPK_API int vpk_pipeline_stage_ms(vpk_ctx* ctx, float ms[4]);
 

@@ -14,7 +14,8 @@ struct PipeState {
     int64_t sumN = 0;
     int S = 0;
     std::vector<int32_t> h_offsets;
-    DBuf seg, lines, offsets, hist, images, sigout, out_small, out_assoc;
+    DBuf seg, lines, offsets, hist, images, sigout, out_small, out_assoc, horizon;
+    HBuf h_horizon;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool have_result = false;
     EmDeviceOut out;
@@ -24,7 +25,7 @@ void pipe_free(vpk_ctx* ctx) {
     if (!ctx->pipe) return;
     PipeState* p = ctx->pipe;
     p->seg.release(); p->lines.release(); p->offsets.release(); p->hist.release(); p->images.release();
-    p->sigout.release(); p->out_small.release(); p->out_assoc.release();
+    p->sigout.release(); p->out_small.release(); p->out_assoc.release(); p->horizon.release(); p->h_horizon.release();
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     delete p;
     ctx->pipe = nullptr;
@@ -144,6 +145,21 @@ int vpk_pipeline_fetch(vpk_ctx* ctx, vpk_em_result* out, float* sigout, uint8_t*
     if (sigout) VPK_CUDA(D2H(sigout, p->sigout.p, B * kCells * sizeof(float)));
     if (sphere_images) VPK_CUDA(D2H(sphere_images, p->images.p, B * (size_t)p->S * p->S));
     VPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VPK_OK;
+}
+
+int vpk_pipeline_horizon(vpk_ctx* ctx, int32_t maxbest, double theta_vmin, double theta_z, double* points, int32_t* best_combo) {
+    if (!ctx || !ctx->pipe || !ctx->pipe->have_result) { set_error("vpk_pipeline_horizon: no completed run"); return VPK_ERR_STATE; }
+    if (!points || !best_combo || maxbest < 0) { set_error("vpk_pipeline_horizon: bad argument"); return VPK_ERR_ARG; }
+    VPK_CUDA(cudaSetDevice(ctx->device));
+    PipeState* p = ctx->pipe;
+    VPK_TRY(p->horizon.ensure(horizon_out_bytes(p->B)));
+    VPK_TRY(p->h_horizon.ensure(horizon_out_bytes(p->B)));
+    // the EM result stays where the EM wrote it: no host round trip between the two
+    VPK_TRY(horizon_dev(ctx, p->out.vp, p->out.counts, p->out.n_vp, p->B, maxbest, theta_vmin, theta_z, p->horizon.p));
+    VPK_CUDA(cudaMemcpyAsync(p->h_horizon.p, p->horizon.p, horizon_out_bytes(p->B), cudaMemcpyDeviceToHost, ctx->stream));
+    VPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    horizon_unpack(p->h_horizon.p, p->B, points, best_combo);
     return VPK_OK;
 }
 

@@ -181,6 +181,12 @@ int em_dev(vpk_ctx* ctx, const double* d_lines, const double* d_segments, const 
            const vpk_em_config* cfg, const EmDeviceOut& out, int phase = 0);
 enum { EM_ALL = 0, EM_EARLY = 1 };
 
+// horizon.cu: calc_horizon.calculate_horizon_and_ortho_vp for a batch of EM results on the device
+int horizon_dev(vpk_ctx* ctx, const double* d_vp, const int32_t* d_counts, const int32_t* d_n_vp, int32_t B, int32_t maxbest,
+                double theta_vmin, double theta_z, void* d_out);
+size_t horizon_out_bytes(int32_t B);
+void horizon_unpack(const void* h_rec, int32_t B, double* points, int32_t* best_combo);
+
 void cnn_free(vpk_ctx* ctx);
 void em_free(vpk_ctx* ctx);
 void pipe_free(vpk_ctx* ctx);

@@ -57,6 +57,17 @@ class Pipeline:
         out = arrs if raw else unpack_results(arrs, self._off)
         return (out, sig, sph) if (want_response or want_sphere) else out
 
+    def horizons(self, maxbest=10, theta_vmin=np.pi / 10., theta_z=np.pi / 4.):
+        """calc_horizon.calculate_horizon_and_ortho_vp (calc_horizon.py:19-225) on the device-resident EM
+        result of the last run(): one (hP1, hP2, zVP, hVP1, hVP2, best_combo) tuple per image."""
+        from . import calc_horizon
+        points = np.empty((self._B, 5, 3), np.float64)
+        combo = np.empty((self._B, 3), np.int32)
+        _lib.check(self.ctx.lib.vpk_pipeline_horizon(self.ctx.h, int(maxbest), float(theta_vmin), float(theta_z),
+                                                     _lib.ptr(points), _lib.ptr(combo)), "vpk_pipeline_horizon")
+        n_vp = np.array([3 if c[2] >= 0 else 0 for c in combo])
+        return calc_horizon._unpack(points, combo, n_vp, 3)
+
     def stage_ms(self):
         ms = (C.c_float * 4)()
         _lib.check(self.ctx.lib.vpk_pipeline_stage_ms(self.ctx.h, ms), "vpk_pipeline_stage_ms")
