@@ -243,6 +243,7 @@ VPK_DEV double seg_len(const Seg& a) {
 VPK_DEV double cos_clipped_multiple(double c, double f) {
     const double kAtClip = 6.123233995736766e-17;
     const double u = 1.0 - fmin(c, 1.0);
+#if !defined(VPK_NO_CHEB)
     if (f == 9.0 && !isnan(c)) {
         if (u > 1.0 - 0.984807753012208) return kAtClip;          // 9 acos(c) > pi/2
         const double t = 1.0 + u * (-81.0 + u * (1080.0 + u * (-5544.0 + u * (14256.0 + u * (-20592.0 + u * (17472.0 + u * (-8640.0 +
@@ -253,6 +254,7 @@ VPK_DEV double cos_clipped_multiple(double c, double f) {
         if (u > 1.0 - 0.7071067811865476) return kAtClip;         // 2 acos(c) > pi/2
         return fmax(1.0 + u * (-4.0 + 2.0 * u), kAtClip);
     }
+#endif
     double dphi = fabs(acos(fmin(fmax(c, -1.0), 1.0)));
     if (isnan(c)) dphi = c;
     return cos(fmin(fmax(f * dphi, -0.5 * kPi), 0.5 * kPi));
@@ -806,7 +808,11 @@ VPK_DEVFN void refit_sums(const Img& im, const double* wrow, const double* wrow2
     mx = warp_max_nanprop(mx);
     any = warp_any(any);
     const bool fit = !(!any || mx == 0.0 || isnan(mx) || isinf(mx));     // :456-460 / LinAlgError
+#if defined(VPK_FORCE_SCALED)
+    if (fit) {
+#else
     if (fit && (mx < 1e-140 || mx > 1e140)) {
+#endif
         // the squares would leave the float64 range: scale the rows first (second sweep, rare)
 #pragma unroll
         for (int k = 0; k < 6; ++k) g[k] = 0.0;

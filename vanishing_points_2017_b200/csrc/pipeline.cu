@@ -2,6 +2,7 @@
 // image -> CNN -> EM (reference example.py:37-39 / benchmark.py:59-66 without
 // the per-image pickles of evaluation.py:183, 289, 328).  All intermediates
 // stay in HBM; only the final per-image results are copied back.
+#include <cstring>
 #include "vpk_internal.cuh"
 
 namespace vpk {
@@ -15,7 +16,7 @@ struct PipeState {
     int S = 0;
     std::vector<int32_t> h_offsets;
     DBuf seg, lines, offsets, hist, images, sigout, out_small, out_assoc, horizon;
-    HBuf h_horizon;
+    HBuf h_horizon, h_small, h_assoc;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool have_result = false;
     EmDeviceOut out;
@@ -25,7 +26,7 @@ void pipe_free(vpk_ctx* ctx) {
     if (!ctx->pipe) return;
     PipeState* p = ctx->pipe;
     p->seg.release(); p->lines.release(); p->offsets.release(); p->hist.release(); p->images.release();
-    p->sigout.release(); p->out_small.release(); p->out_assoc.release(); p->horizon.release(); p->h_horizon.release();
+    p->sigout.release(); p->out_small.release(); p->out_assoc.release(); p->horizon.release(); p->h_horizon.release(); p->h_small.release(); p->h_assoc.release();
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     delete p;
     ctx->pipe = nullptr;
@@ -133,18 +134,30 @@ int vpk_pipeline_fetch(vpk_ctx* ctx, vpk_em_result* out, float* sigout, uint8_t*
         if (!out->status || !out->n_vp || !out->iterations || !out->vp || !out->sigma || !out->counts || !out->counts_weighted || !out->vp_assoc) {
             set_error("vpk_pipeline_fetch: result arrays must be allocated by the caller"); return VPK_ERR_ARG;
         }
-        VPK_CUDA(D2H(out->vp, p->out.vp, B * VPK_MAX_VP * 3 * sizeof(double)));
-        VPK_CUDA(D2H(out->sigma, p->out.sigma, B * VPK_MAX_VP * sizeof(double)));
-        VPK_CUDA(D2H(out->counts_weighted, p->out.counts_weighted, B * VPK_MAX_VP * sizeof(double)));
-        VPK_CUDA(D2H(out->status, p->out.status, B * sizeof(int32_t)));
-        VPK_CUDA(D2H(out->n_vp, p->out.n_vp, B * sizeof(int32_t)));
-        VPK_CUDA(D2H(out->iterations, p->out.iterations, B * sizeof(int32_t)));
-        VPK_CUDA(D2H(out->counts, p->out.counts, B * VPK_MAX_VP * sizeof(int32_t)));
-        if (p->sumN) VPK_CUDA(D2H(out->vp_assoc, p->out.vp_assoc, p->sumN * sizeof(int32_t)));
+        // the small outputs are one packed block on the device (vp | sigma | counts_weighted | status |
+        // n_vp | iterations | counts): one copy into pinned staging instead of seven into pageable memory
+        const size_t n_f64 = B * VPK_MAX_VP * 5, n_i32 = 3 * B + B * VPK_MAX_VP;
+        const size_t small_bytes = n_f64 * sizeof(double) + n_i32 * sizeof(int32_t);
+        VPK_TRY(p->h_small.ensure(small_bytes));
+        VPK_TRY(p->h_assoc.ensure((p->sumN + 1) * sizeof(int32_t)));
+        VPK_CUDA(D2H(p->h_small.p, p->out_small.p, small_bytes));
+        if (p->sumN) VPK_CUDA(D2H(p->h_assoc.p, p->out.vp_assoc, p->sumN * sizeof(int32_t)));
     }
     if (sigout) VPK_CUDA(D2H(sigout, p->sigout.p, B * kCells * sizeof(float)));
     if (sphere_images) VPK_CUDA(D2H(sphere_images, p->images.p, B * (size_t)p->S * p->S));
     VPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (out) {
+        const double* f = p->h_small.as<double>();
+        memcpy(out->vp, f, B * VPK_MAX_VP * 3 * sizeof(double)); f += B * VPK_MAX_VP * 3;
+        memcpy(out->sigma, f, B * VPK_MAX_VP * sizeof(double)); f += B * VPK_MAX_VP;
+        memcpy(out->counts_weighted, f, B * VPK_MAX_VP * sizeof(double)); f += B * VPK_MAX_VP;
+        const int32_t* ip = reinterpret_cast<const int32_t*>(f);
+        memcpy(out->status, ip, B * sizeof(int32_t)); ip += B;
+        memcpy(out->n_vp, ip, B * sizeof(int32_t)); ip += B;
+        memcpy(out->iterations, ip, B * sizeof(int32_t)); ip += B;
+        memcpy(out->counts, ip, B * VPK_MAX_VP * sizeof(int32_t));
+        if (p->sumN) memcpy(out->vp_assoc, p->h_assoc.p, p->sumN * sizeof(int32_t));
+    }
     return VPK_OK;
 }
 

@@ -73,11 +73,21 @@ class Pipeline:
         _lib.check(self.ctx.lib.vpk_pipeline_stage_ms(self.ctx.h, ms), "vpk_pipeline_stage_ms")
         return {"sphere": ms[0], "cnn": ms[1], "em": ms[2], "total": ms[3]}
 
-    def __call__(self, segments, offsets, **fetch_kw):
-        """End to end from host buffers (H2D, path, D2H)."""
-        self.upload(segments, offsets)
-        self.run()
-        return self.fetch(**fetch_kw)
+    def __call__(self, segments, offsets, want_response=False, want_sphere=False, raw=False):
+        """End to end from host buffers in ONE library call (vpk_pipeline_host: H2D, path, D2H)."""
+        seg = _lib.as_f64(segments, 4)
+        off = _lib.as_offsets(offsets)
+        if off[-1] != seg.shape[0]:
+            raise ValueError("offsets[-1] must equal the number of segments")
+        self._B, self._off = off.size - 1, off
+        arrs, res = _alloc_result(self._B, int(off[-1]), False)
+        sig = np.empty((self._B, 20, 20), np.float32) if want_response else None
+        sph = np.empty((self._B, self.size, self.size), np.uint8) if want_sphere else None
+        _lib.check(self.ctx.lib.vpk_pipeline_host(self.ctx.h, _lib.ptr(seg), _lib.ptr(off), self._B, self.size, self.mode,
+                                                  self.alpha, C.byref(self.cfg), C.byref(res), _lib.ptr(sig), _lib.ptr(sph)),
+                   "vpk_pipeline_host")
+        out = arrs if raw else unpack_results(arrs, self._off)
+        return (out, sig, sph) if (want_response or want_sphere) else out
 
 
 def image_cost(n):

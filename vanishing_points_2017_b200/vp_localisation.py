@@ -20,10 +20,11 @@ _SKELETON = {"vp_assoc": None, "vp": None, "counts": None, "count_id": None, "de
 def _alloc_result(B, sumN, want_dm):
     M = _lib.VPK_MAX_VP
     arrs = {
-        "status": np.zeros(B, np.int32), "n_vp": np.zeros(B, np.int32), "iterations": np.zeros(B, np.int32),
-        "vp": np.zeros((B, M, 3), np.float64), "sigma": np.zeros((B, M), np.float64),
-        "counts": np.zeros((B, M), np.int32), "counts_weighted": np.zeros((B, M), np.float64),
-        "vp_assoc": np.zeros(max(sumN, 1), np.int32),
+        # every entry the caller reads is written by the library (rows beyond n_vp are never read)
+        "status": np.empty(B, np.int32), "n_vp": np.empty(B, np.int32), "iterations": np.empty(B, np.int32),
+        "vp": np.empty((B, M, 3), np.float64), "sigma": np.empty((B, M), np.float64),
+        "counts": np.empty((B, M), np.int32), "counts_weighted": np.empty((B, M), np.float64),
+        "vp_assoc": np.empty(max(sumN, 1), np.int32),
         "decision_metric": np.zeros(max(M * sumN, 1), np.float64) if want_dm else None,
     }
     res = _lib.EmResult()
