@@ -71,3 +71,23 @@ extern "C" int hostsim_em(const double* lines, const double* segs, int N, const 
     delete st; delete isc; delete sc;
     return active ? 1 : 0;
 }
+
+// One refit (E7, calc_new_vanishing_point): unit lines `ln` (N,3), weights `w` (N) -> vp (3).
+// Returns 1 if a VP was produced, 0 otherwise; *refined = 1 if the ill-conditioned path ran.
+extern "C" int hostsim_refit(const double* ln, const double* w, int N, double* vp, int* refined) {
+    const Team T = make_team();
+    std::vector<double> ws(slot_doubles(N) + 16, 0.0);
+    std::vector<double> segs(4 * (size_t)N + 4, 0.0);
+    Img im = make_img(N, ws.data(), segs.data());
+    for (int n = 0; n < N; ++n) {
+        for (int k = 0; k < 3; ++k) im.ln[3 * (size_t)n + k] = ln[3 * (size_t)n + k];
+        im.w[n] = w[n];
+        im.pvl[n] = 1.0; im.lvsq[n] = 0.0;
+    }
+    std::vector<RefitAcc> acc(kMaxM);
+    refit_sums(im, im.w, nullptr, -1, 0, -1, acc[0], T);
+    refit_finish(acc.data(), 1, im, im.w, (size_t)N, nullptr, false, T);
+    for (int k = 0; k < 3; ++k) vp[k] = acc[0].nv[k];
+    *refined = acc[0].refine;
+    return acc[0].ok;
+}

@@ -103,3 +103,42 @@ def test_state_machine_kwargs(sim):
     iv = sc["vps"] * 3.0
     ref = vo.expectation_maximisation(sc["lines"].copy(), sc["segments"].copy(), resp.copy(), sphere_image=img, init_vp=iv)
     compare(sim(sc["lines"], sc["segments"], resp, img, init_vp=iv), ref)
+
+
+def test_refit_matches_svd_also_when_one_line_dominates(sim):
+    """E7: the smallest right-singular vector of diag(w / max w) l (vp_localisation.py:453-479, LAPACK SVD
+    in the reference) from the 3x3 scatter matrix.  When one line dominates, the scatter matrix in the
+    original basis loses the small singular values; the refinement sweep must recover the SVD's answer."""
+    lib = C.CDLL(SO)
+    lib.hostsim_refit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    rs = np.random.RandomState(5)
+    n_refined = 0
+    for case in range(60):
+        N = int(rs.randint(3, 40))
+        l = rs.standard_normal((N, 3))
+        l /= np.linalg.norm(l, axis=1, keepdims=True)
+        w = rs.uniform(0.05, 1.0, N)
+        if case % 3 == 1:
+            w *= 10.0 ** -rs.uniform(4, 7)            # one line dominates: sigma_2 / sigma_1 ~ 1e-4 .. 1e-7
+            w[rs.randint(N)] = 1.0
+        elif case % 3 == 2:
+            vp_true = rs.standard_normal(3)
+            vp_true /= np.linalg.norm(vp_true)        # lines through one point + one dominant line
+            l = np.cross(vp_true, rs.standard_normal((N, 3)))
+            l += 1e-9 * rs.standard_normal((N, 3))
+            l /= np.linalg.norm(l, axis=1, keepdims=True)
+            w *= 1e-5
+            w[0] = 1.0
+        A = (w / w.max())[:, None] * l
+        ref = np.linalg.svd(A, full_matrices=False)[2][2]
+        ref = ref * np.sign(ref[2])
+        sv = np.linalg.svd(A, compute_uv=False)
+        vp, refined = np.zeros(3), np.zeros(1, np.int32)
+        ok = lib.hostsim_refit(_lib.ptr(np.ascontiguousarray(l)), _lib.ptr(np.ascontiguousarray(w)), N, _lib.ptr(vp), _lib.ptr(refined))
+        assert ok == 1
+        n_refined += int(refined[0])
+        ang = np.arccos(min(abs(float(vp @ ref)), 1.0))
+        # the SVD itself is only defined to eps * sigma_1 / (sigma_2 - sigma_3)
+        bound = max(1e-6, 1e3 * 2.2e-16 * sv[0] / max(sv[1] - sv[2], 1e-300))
+        assert ang < bound, (case, ang, bound, sv, int(refined[0]))
+    assert n_refined >= 10

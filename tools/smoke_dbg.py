@@ -18,3 +18,12 @@ for b in range(3):
     if res[b]["vp"] is not None and ref["vp"] is not None:
         print("  ours vp\n", res[b]["vp"], "\n  ref vp\n", ref["vp"])
         print("  ours sigma", res[b]["sigma"], "ref sigma", ref["sigma"])
+import os
+os.makedirs("gpurun_out", exist_ok=True)
+out = {"seg": seg, "off": off, "sig": sig, "sph": sph}
+for b, r in enumerate(res):
+    if r["vp"] is not None:
+        for k in ("vp", "counts", "vp_assoc", "sigma"):
+            out["%s_%d" % (k, b)] = r[k]
+        out["iter_%d" % b] = np.array(r["iterations"])
+np.savez_compressed("gpurun_out/smoke_case.npz", **out)

@@ -367,11 +367,14 @@ VPK_DEV void knn_insert(double* kd, int* kj, int stride, int& cnt, double d, int
 }
 
 // ---------------------------------------------------------------------------
-// eigenvector of the smallest eigenvalue of the symmetric 3x3 matrix
-// [g0 g1 g2; g1 g3 g4; g2 g4 g5] (cyclic Jacobi, float64).  false if not finite.
+// Eigen-decomposition of the symmetric 3x3 matrix [g0 g1 g2; g1 g3 g4; g2 g4 g5] (cyclic Jacobi,
+// float64): eigenvalues ascending in eval (scaled by 1 / trace), eigenvectors in the columns of evec
+// in the same order.  false if not finite.  relative: stop on |a_pq| <= 1e-16 sqrt(a_pp a_qq) instead of
+// an absolute threshold -- Jacobi then resolves the small eigenpairs of a GRADED matrix to high relative
+// accuracy (Demmel & Veselic), which the refinement of ill-conditioned fits below relies on.
 // Replaces SVD(diag(w) l) of calc_new_vanishing_point (vp_localisation.py:453-479).
 // ---------------------------------------------------------------------------
-VPK_DEVFN bool smallest_eigvec3(const double g[6], double out[3]) {
+VPK_DEVFN bool jacobi_eig3(const double g[6], bool relative, double evec[3][3], double eval[3]) {
     double tr = g[0] + g[3] + g[5];
     if (!(tr > 0.0) || isinf(tr)) return false;
     double sc = 1.0 / tr;
@@ -380,9 +383,15 @@ VPK_DEVFN bool smallest_eigvec3(const double g[6], double out[3]) {
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j)
             if (isnan(a[i][j])) return false;
-    for (int sweep = 0; sweep < 24; ++sweep) {
-        double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
-        if (off < 1e-36) break;                 // off-diagonal below 1e-18 of the trace: converged in float64
+    for (int sweep = 0; sweep < (relative ? 40 : 24); ++sweep) {
+        if (relative) {
+            const double tol = 1e-32;
+            if (a[0][1] * a[0][1] <= tol * fabs(a[0][0] * a[1][1]) && a[0][2] * a[0][2] <= tol * fabs(a[0][0] * a[2][2]) &&
+                a[1][2] * a[1][2] <= tol * fabs(a[1][1] * a[2][2])) break;
+        } else {
+            double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+            if (off < 1e-36) break;             // off-diagonal below 1e-18 of the trace: converged in float64
+        }
 #pragma unroll
         for (int pq = 0; pq < 3; ++pq) {
             const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
@@ -410,14 +419,32 @@ VPK_DEVFN bool smallest_eigvec3(const double g[6], double out[3]) {
             }
         }
     }
-    // column of the smallest diagonal entry (first one on ties); selects instead of dynamic indexing
-    int m = 0;
-    double dm = a[0][0];
-    if (a[1][1] < dm) { m = 1; dm = a[1][1]; }
-    if (a[2][2] < dm) m = 2;
-    const double x = m == 0 ? v[0][0] : (m == 1 ? v[0][1] : v[0][2]);
-    const double y = m == 0 ? v[1][0] : (m == 1 ? v[1][1] : v[1][2]);
-    const double z = m == 0 ? v[2][0] : (m == 1 ? v[2][1] : v[2][2]);
+    // ascending order of the diagonal (first one on ties); selects instead of dynamic indexing
+    const double d0 = a[0][0], d1 = a[1][1], d2 = a[2][2];
+    int lo = 0;
+    if (d1 < d0) lo = 1;
+    if (d2 < (lo == 0 ? d0 : d1)) lo = 2;
+    int hi = lo == 0 ? 1 : 0;                                   // largest of the other two (first on ties)
+    {
+        const int o1 = lo == 0 ? 1 : 0, o2 = lo == 2 ? 1 : 2;
+        const double e1 = o1 == 0 ? d0 : d1, e2 = o2 == 1 ? d1 : d2;
+        hi = e2 > e1 ? o2 : o1;
+    }
+    const int mid = 3 - lo - hi;
+    const int order[3] = {lo, mid, hi};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int m = order[c];
+        eval[c] = m == 0 ? d0 : (m == 1 ? d1 : d2);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) evec[k][c] = m == 0 ? v[k][0] : (m == 1 ? v[k][1] : v[k][2]);
+    }
+    return true;
+}
+VPK_DEVFN bool smallest_eigvec3(const double g[6], double out[3]) {
+    double evec[3][3], eval[3];
+    if (!jacobi_eig3(g, false, evec, eval)) return false;
+    const double x = evec[0][0], y = evec[1][0], z = evec[2][0];
     double n = sqrt(x * x + y * y + z * z);
     if (!(n > 0.0)) return false;
     out[0] = x / n; out[1] = y / n; out[2] = z / n;
@@ -772,7 +799,8 @@ VPK_DEVFN void line_counts(const Img& im, EmSlot& st, double thresh, const Team&
 struct RefitAcc {
     double g[6], num, den, a1[3];      // a1: the only selected row, scaled (rows == 1)
     double nv[3], sv;                  // results
-    int rows, fit, any, ok;
+    double q[6];                       // refinement: the other two eigenvectors of the first solve
+    int rows, fit, any, ok, refine;
 };
 VPK_DEVFN void refit_sums(const Img& im, const double* wrow, const double* wrow2, int sel, int vm, int vm2, RefitAcc& acc,
                           const Team& T) {
@@ -844,8 +872,18 @@ VPK_DEVFN void refit_sums(const Img& im, const double* wrow, const double* wrow2
         }
     }
 }
+// The 3x3 scatter matrix squares the singular values of diag(w / max w) l.  When one line dominates the
+// fit (sigma_2 / sigma_1 tiny: a hypothesis supported by very few lines) the smallest eigenvector of the
+// matrix formed in the ORIGINAL basis is only good to eps * lambda_1 / (lambda_2 - lambda_3), far worse than
+// the reference's SVD.  Such fits are refined: a second sweep forms the scatter matrix in the eigenbasis
+// of the first solve -- there it is graded, its small entries are sums of small numbers instead of
+// differences of large ones -- and a Jacobi solve with a relative stopping rule resolves the small
+// eigenpair to high relative accuracy.
+constexpr double kRefineGap = 1e-9;    // refine if (lambda_2 - lambda_3) < kRefineGap * lambda_1 (first solve worse than ~1e-7 rad)
+
 VPK_DEVFN void refit_solve(RefitAcc& acc) {
     acc.ok = 0;
+    acc.refine = 0;
     if (!acc.fit) return;
     double e[3];
     bool okv;
@@ -863,15 +901,67 @@ VPK_DEVFN void refit_solve(RefitAcc& acc) {
         okv = n2 > 0.0 && !isnan(n2);
         if (okv) { e[0] /= n2; e[1] /= n2; e[2] /= n2; }
     } else {
-        okv = smallest_eigvec3(acc.g, e);
+        double evec[3][3], eval[3];
+        okv = jacobi_eig3(acc.g, false, evec, eval);
+        if (okv) {
+            const double n = sqrt(evec[0][0] * evec[0][0] + evec[1][0] * evec[1][0] + evec[2][0] * evec[2][0]);
+            okv = n > 0.0;
+            if (okv) {
+                e[0] = evec[0][0] / n; e[1] = evec[1][0] / n; e[2] = evec[2][0] / n;
+                if (eval[1] - eval[0] < kRefineGap * eval[2]) {
+                    acc.refine = 1;
+                    for (int k = 0; k < 3; ++k) { acc.q[k] = evec[k][2]; acc.q[3 + k] = evec[k][1]; }
+                }
+            }
+        }
     }
     if (!okv) return;
+    if (acc.refine) { acc.nv[0] = e[0]; acc.nv[1] = e[1]; acc.nv[2] = e[2]; acc.ok = 1; return; }   // sign after the refinement
     double sg = sign_np(e[2]);                                           // :474
     acc.nv[0] = e[0] * sg; acc.nv[1] = e[1] * sg; acc.nv[2] = e[2] * sg;
     acc.ok = 1;
 }
-// the scalar tails of `count` refits: thread q < kMaxM solves VP q, thread kMaxM + q evaluates its sigma
-VPK_DEVFN void refit_finish(RefitAcc* acc, int count, const Team& T) {
+// second sweep of a refined fit (one warp): scatter matrix of the selected rows in the basis (q1, q2, nv)
+VPK_DEVFN void refit_sums_rotated(const Img& im, const double* wrow, const double* wrow2, int sel, RefitAcc& acc, const Team& T) {
+    const int N = im.N;
+    const double q1[3] = {acc.q[0], acc.q[1], acc.q[2]}, q2[3] = {acc.q[3], acc.q[4], acc.q[5]},
+                 q3[3] = {acc.nv[0], acc.nv[1], acc.nv[2]};
+    double g[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 4
+    for (int n = T.lane; n < N; n += T.lanes) {
+        if (!(sel < 0 || im.assoc[n] == sel)) continue;
+        const double x = wrow[n] + (wrow2 ? wrow2[n] : 0.0);
+        const double l0 = im.ln[3 * (size_t)n], l1 = im.ln[3 * (size_t)n + 1], l2 = im.ln[3 * (size_t)n + 2];
+        const double a = x * (l0 * q1[0] + l1 * q1[1] + l2 * q1[2]), b = x * (l0 * q2[0] + l1 * q2[1] + l2 * q2[2]),
+                     c = x * (l0 * q3[0] + l1 * q3[1] + l2 * q3[2]);
+        g[0] += a * a; g[1] += a * b; g[2] += a * c; g[3] += b * b; g[4] += b * c; g[5] += c * c;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) g[k] = warp_sum(g[k]);
+    if (T.lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc.g[k] = g[k];
+    }
+}
+VPK_DEVFN void refit_refine(RefitAcc& acc) {
+    double evec[3][3], eval[3];
+    double e[3] = {acc.nv[0], acc.nv[1], acc.nv[2]};
+    if (jacobi_eig3(acc.g, true, evec, eval)) {
+        // smallest eigenvector in the rotated basis -> original coordinates
+        const double c1 = evec[0][0], c2 = evec[1][0], c3 = evec[2][0];
+        double r[3];
+        for (int k = 0; k < 3; ++k) r[k] = c1 * acc.q[k] + c2 * acc.q[3 + k] + c3 * acc.nv[k];
+        const double n = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+        if (n > 0.0 && !isnan(n)) { e[0] = r[0] / n; e[1] = r[1] / n; e[2] = r[2] / n; }
+    }
+    double sg = sign_np(e[2]);                                           // :474
+    acc.nv[0] = e[0] * sg; acc.nv[1] = e[1] * sg; acc.nv[2] = e[2] * sg;
+}
+// the scalar tails of `count` refits: thread q < kMaxM solves VP q, thread kMaxM + q evaluates its sigma;
+// then the refinement of the ill-conditioned ones.  Fit m uses the weight row w0 + m * stride (+ w1, merge)
+// and, hard = true, only the lines assigned to VP m.
+VPK_DEVFN void refit_finish(RefitAcc* acc, int count, const Img& im, const double* w0, size_t stride, const double* w1, bool hard,
+                            const Team& T) {
     team_sync();
     for (int q = T.tid; q < 2 * kMaxM; q += T.nthreads) {
         const int m = q % kMaxM;
@@ -879,6 +969,15 @@ VPK_DEVFN void refit_finish(RefitAcc* acc, int count, const Team& T) {
         if (q < kMaxM) refit_solve(acc[m]);
         else acc[m].sv = exp(log(acc[m].num) - log(acc[m].den));
     }
+    team_sync();
+    bool any = false;
+    for (int m = 0; m < count; ++m) any = any || acc[m].refine != 0;
+    if (!any) return;
+    for (int m = T.warp; m < count; m += T.nwarps)
+        if (acc[m].refine) refit_sums_rotated(im, w0 + (size_t)m * stride, w1, hard ? m : -1, acc[m], T);
+    team_sync();
+    for (int m = T.tid; m < count; m += T.nthreads)
+        if (acc[m].refine) refit_refine(acc[m]);
     team_sync();
 }
 
@@ -1332,7 +1431,7 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
                 for (int m = T.warp; m < M; m += T.nwarps) refit_sums(im, im.w + (size_t)m * N, nullptr, -1, m, -1, acc[m], T);
                 team_sync();
                 VPK_MARK(sc, T, 2);
-                refit_finish(acc, M, T);
+                refit_finish(acc, M, im, im.w, (size_t)N, nullptr, false, T);
                 VPK_MARK(sc, T, 3);
             }
             for (int m = T.tid; m < M; m += T.nthreads) {
@@ -1439,7 +1538,7 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
             const int j = st.merge_j, k = st.merge_k, M = st.M;
             RefitAcc* acc = refit_acc(sc);
             if (T.warp == 0) refit_sums(im, im.w + (size_t)j * N, im.w + (size_t)k * N, -1, k, j, acc[0], T);
-            refit_finish(acc, 1, T);
+            refit_finish(acc, 1, im, im.w + (size_t)j * N, (size_t)N, im.w + (size_t)k * N, false, T);
             if (T.tid == 0) {
                 const double sk = acc[0].sv;
                 st.s[k] = sk;                                  // assigned before the test (:666)
@@ -1472,7 +1571,7 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
             const int M2 = st.M;
             RefitAcc* acc = refit_acc(sc);
             for (int m = T.warp; m < M2; m += T.nwarps) refit_sums(im, im.w + (size_t)m * N, nullptr, m, m, -1, acc[m], T);
-            refit_finish(acc, M2, T);
+            refit_finish(acc, M2, im, im.w, (size_t)N, nullptr, true, T);
             for (int m = T.tid; m < M2; m += T.nthreads) {
                 if (!acc[m].any) { sc.rem[m] = 0; continue; }              // no line assigned: left as it is (:354-356)
                 int rem = 0;
