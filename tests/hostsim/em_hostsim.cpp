@@ -86,7 +86,8 @@ extern "C" int hostsim_refit(const double* ln, const double* w, int N, double* v
     }
     std::vector<RefitAcc> acc(kMaxM);
     refit_sums(im, im.w, nullptr, -1, 0, -1, acc[0], T);
-    refit_finish(acc.data(), 1, im, im.w, (size_t)N, nullptr, false, T);
+    int any_refine = 0;
+    refit_finish(acc.data(), 1, im, im.w, (size_t)N, nullptr, false, any_refine, T);
     for (int k = 0; k < 3; ++k) vp[k] = acc[0].nv[k];
     *refined = acc[0].refine;
     return acc[0].ok;

@@ -464,7 +464,7 @@ struct PostScratch {
     int l_nflag;
     double ang[kMaxM], err[kMaxM], nv[kMaxM][3];
     int ok[kMaxM], rem[kMaxM];
-    int ia, ib, flag;
+    int ia, ib, flag, flag2;
     double da;
 #if defined(VPK_EM_MARKS)
     long long mark[16], mark_t;        // cycles of thread 0 between the markers of post_slot (diagnostic builds)
@@ -961,18 +961,19 @@ VPK_DEVFN void refit_refine(RefitAcc& acc) {
 // then the refinement of the ill-conditioned ones.  Fit m uses the weight row w0 + m * stride (+ w1, merge)
 // and, hard = true, only the lines assigned to VP m.
 VPK_DEVFN void refit_finish(RefitAcc* acc, int count, const Img& im, const double* w0, size_t stride, const double* w1, bool hard,
-                            const Team& T) {
+                            int& any_refine, const Team& T) {
+    if (T.tid == 0) any_refine = 0;
     team_sync();
     for (int q = T.tid; q < 2 * kMaxM; q += T.nthreads) {
         const int m = q % kMaxM;
         if (m >= count) continue;
-        if (q < kMaxM) refit_solve(acc[m]);
-        else acc[m].sv = exp(log(acc[m].num) - log(acc[m].den));
+        if (q < kMaxM) {
+            refit_solve(acc[m]);
+            if (acc[m].refine) any_refine = 1;
+        } else acc[m].sv = exp(log(acc[m].num) - log(acc[m].den));
     }
     team_sync();
-    bool any = false;
-    for (int m = 0; m < count; ++m) any = any || acc[m].refine != 0;
-    if (!any) return;
+    if (!any_refine) return;
     for (int m = T.warp; m < count; m += T.nwarps)
         if (acc[m].refine) refit_sums_rotated(im, w0 + (size_t)m * stride, w1, hard ? m : -1, acc[m], T);
     team_sync();
@@ -1431,7 +1432,7 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
                 for (int m = T.warp; m < M; m += T.nwarps) refit_sums(im, im.w + (size_t)m * N, nullptr, -1, m, -1, acc[m], T);
                 team_sync();
                 VPK_MARK(sc, T, 2);
-                refit_finish(acc, M, im, im.w, (size_t)N, nullptr, false, T);
+                refit_finish(acc, M, im, im.w, (size_t)N, nullptr, false, sc.flag2, T);
                 VPK_MARK(sc, T, 3);
             }
             for (int m = T.tid; m < M; m += T.nthreads) {
@@ -1538,7 +1539,7 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
             const int j = st.merge_j, k = st.merge_k, M = st.M;
             RefitAcc* acc = refit_acc(sc);
             if (T.warp == 0) refit_sums(im, im.w + (size_t)j * N, im.w + (size_t)k * N, -1, k, j, acc[0], T);
-            refit_finish(acc, 1, im, im.w + (size_t)j * N, (size_t)N, im.w + (size_t)k * N, false, T);
+            refit_finish(acc, 1, im, im.w + (size_t)j * N, (size_t)N, im.w + (size_t)k * N, false, sc.flag2, T);
             if (T.tid == 0) {
                 const double sk = acc[0].sv;
                 st.s[k] = sk;                                  // assigned before the test (:666)
@@ -1571,7 +1572,7 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
             const int M2 = st.M;
             RefitAcc* acc = refit_acc(sc);
             for (int m = T.warp; m < M2; m += T.nwarps) refit_sums(im, im.w + (size_t)m * N, nullptr, m, m, -1, acc[m], T);
-            refit_finish(acc, M2, im, im.w, (size_t)N, nullptr, true, T);
+            refit_finish(acc, M2, im, im.w, (size_t)N, nullptr, true, sc.flag2, T);
             for (int m = T.tid; m < M2; m += T.nthreads) {
                 if (!acc[m].any) { sc.rem[m] = 0; continue; }              // no line assigned: left as it is (:354-356)
                 int rem = 0;
