@@ -344,6 +344,14 @@ def run_ours(args, rank, world, local_rank):
                      "frac": ach / peaks["hbm_gbs"]}
             r.update({"traffic": ncu_traffic(name, kname), "kernel": kname, "avg_launch_ms": avg_ms,
                       "peak_source": peaks["_source"]})
+            if not kname.startswith("gemm_"):
+                r["algorithmic_bytes_per_launch"] = byt
+            if kname in ("em_wmat", "em_post", "em_estep") and r["traffic"] is not None:
+                # `achieved` averages over every superstep of the run (late ones have few active images);
+                # the ncu capture behind `traffic` is of supersteps 10-12, where all images are active
+                full = {"em_wmat": float(np.sum(8.0 * n * n))}.get(kname)
+                r["traffic_note"] = ("ncu capture of supersteps 10-12 (every image active)" +
+                                     ("; algorithmic bytes of those launches: %.0f" % full if full else ""))
             return r
 
         if top[0] is not None:

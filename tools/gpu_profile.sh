@@ -16,3 +16,7 @@ ncu --set full --clock-control none --import-source on -k regex:"em_(estep|wmat|
 ncu --set full --clock-control none --import-source on -k regex:"em_pair|em_init|sphere_votes|gemm_bf16|splitk|lrn_pool|votes_image|plane_max|conv1_operand" -c 20 \
     -o gpurun_out/${TAG}_once -f python tools/run_once.py --runs 1 > gpurun_out/${TAG}_once.log 2>&1
 ls -la gpurun_out | tail -8
+# summarise on the box and drop the reports (gpurun_out/ may carry at most 64 MiB back)
+python tools/ncu_summary.py gpurun_out/${TAG}_em_steps.ncu-rep gpurun_out/${TAG}_ncu_full_em_supersteps.csv
+python tools/ncu_summary.py gpurun_out/${TAG}_once.ncu-rep gpurun_out/${TAG}_ncu_full_once_kernels.csv
+if [ -z "$KEEP_NCU_REP" ]; then rm -f gpurun_out/${TAG}_em_steps.ncu-rep gpurun_out/${TAG}_once.ncu-rep; fi
