@@ -131,9 +131,21 @@ __global__ void plane_max_kernel(const T* __restrict__ h, int64_t plane, unsigne
     const int b = blockIdx.y;
     const T* p = h + (int64_t)b * plane;
     unsigned long long m = 0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < plane; i += (int64_t)gridDim.x * blockDim.x) {
-        unsigned long long v = (unsigned long long)p[i];
-        m = v > m ? v : m;
+    constexpr int V = 16 / sizeof(T);                      // elements per 16-byte load
+    const bool vec = ((plane * sizeof(T)) % 16 == 0) && (reinterpret_cast<uintptr_t>(p) % 16 == 0);
+    if (vec) {
+        const int64_t nv = plane / V;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+            const uint4 q = reinterpret_cast<const uint4*>(p)[i];
+            const T* e = reinterpret_cast<const T*>(&q);
+#pragma unroll
+            for (int k = 0; k < V; ++k) { const unsigned long long v = (unsigned long long)e[k]; m = v > m ? v : m; }
+        }
+    } else {
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < plane; i += (int64_t)gridDim.x * blockDim.x) {
+            unsigned long long v = (unsigned long long)p[i];
+            m = v > m ? v : m;
+        }
     }
     for (int o = 16; o > 0; o >>= 1) {
         unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
@@ -142,15 +154,39 @@ __global__ void plane_max_kernel(const T* __restrict__ h, int64_t plane, unsigne
     if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxv + b, m);
 }
 
+// floor(255 v / m) in exact integer arithmetic (32-bit division when it cannot overflow)
+__device__ __forceinline__ uint8_t scale_to_u8(unsigned long long v, unsigned long long m) {
+    if (m == 0) return 0;
+    if (m <= 0x00ffffffull) return (uint8_t)(((uint32_t)v * 255u) / (uint32_t)m);      // v <= m < 2^24: 255 v < 2^32
+    return (uint8_t)((v * 255ull) / m);
+}
+
 // image = floor(255*h/max) in exact integer arithmetic; optional float export
 template <typename T>
 __global__ void votes_image_kernel(const T* __restrict__ h, int64_t plane, const unsigned long long* __restrict__ maxv,
                                    uint8_t* __restrict__ img, float* __restrict__ wout) {
     const int b = blockIdx.y;
     const unsigned long long m = maxv[b];
+    const T* p = h + (int64_t)b * plane;
+    // uint32 counts, image only: 16 pixels per thread (four 16-byte loads, one 16-byte store)
+    if (sizeof(T) == 4 && img && !wout && plane % 16 == 0 && reinterpret_cast<uintptr_t>(p) % 16 == 0 &&
+        reinterpret_cast<uintptr_t>(img + (int64_t)b * plane) % 16 == 0) {
+        const int64_t nv = plane / 16;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint4 v = reinterpret_cast<const uint4*>(p)[4 * i + q];
+                o[q] = (uint32_t)scale_to_u8(v.x, m) | ((uint32_t)scale_to_u8(v.y, m) << 8) | ((uint32_t)scale_to_u8(v.z, m) << 16) |
+                       ((uint32_t)scale_to_u8(v.w, m) << 24);
+            }
+            reinterpret_cast<uint4*>(img + (int64_t)b * plane)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        return;
+    }
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < plane; i += (int64_t)gridDim.x * blockDim.x) {
-        unsigned long long v = (unsigned long long)h[(int64_t)b * plane + i];
-        if (img) img[(int64_t)b * plane + i] = m ? (uint8_t)((v * 255ull) / m) : (uint8_t)0;
+        unsigned long long v = (unsigned long long)p[i];
+        if (img) img[(int64_t)b * plane + i] = scale_to_u8(v, m);
         if (wout) wout[(int64_t)b * plane + i] = (float)((double)v * (1.0 / 65536.0));
     }
 }
@@ -273,9 +309,13 @@ int sphere_map_dev(vpk_ctx* ctx, const double* d_lines, const int32_t* d_offsets
         if (weighted) VPK_CUDA(cudaMemsetAsync(d_whist, 0, sizeof(unsigned long long) * plane * B, ctx->stream));
         else VPK_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * plane * B, ctx->stream));
         if (items > 0) {
-            VPK_TRY(ctx->h_stage.ensure(items * sizeof(int4)));
+            const int turn = ctx->work_turn;
+            ctx->work_turn ^= 1;
+            if (!ctx->ev_work[turn]) VPK_CUDA(cudaEventCreateWithFlags(&ctx->ev_work[turn], cudaEventDisableTiming));
+            else VPK_CUDA(cudaEventSynchronize(ctx->ev_work[turn]));      // the copy out of this buffer two calls ago
+            VPK_TRY(ctx->h_work[turn].ensure(items * sizeof(int4)));
             VPK_TRY(ctx->d_work.ensure(items * sizeof(int4)));
-            int4* w = ctx->h_stage.as<int4>();
+            int4* w = ctx->h_work[turn].as<int4>();
             int64_t k = 0;
             for (int b = 0; b < B; ++b) {
                 int T = (h_offsets[b + 1] - h_offsets[b] + kTile - 1) / kTile;
@@ -283,14 +323,13 @@ int sphere_map_dev(vpk_ctx* ctx, const double* d_lines, const int32_t* d_offsets
                     for (int tj = ti; tj < T; ++tj) w[k++] = make_int4(b, ti, tj, 0);
             }
             VPK_CUDA(cudaMemcpyAsync(ctx->d_work.p, w, items * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+            VPK_CUDA(cudaEventRecord(ctx->ev_work[turn], ctx->stream));
             {
                 KernelScope ks(ctx, "sphere_votes");
                 sphere_votes_kernel<<<(unsigned)items, kVoteThreads, 0, ctx->stream>>>(
                     d_lines, d_offsets, ctx->d_work.as<int4>(), S, d_weights, d_hist, d_whist);
                 VPK_TRY(check_launch("sphere_votes"));
             }
-            // the pinned work list must not be rewritten before the copy has run
-            VPK_CUDA(cudaStreamSynchronize(ctx->stream));
         }
         return VPK_OK;
     }
