@@ -2,6 +2,9 @@
 // image -> CNN -> EM (reference example.py:37-39 / benchmark.py:59-66 without
 // the per-image pickles of evaluation.py:183, 289, 328).  All intermediates
 // stay in HBM; only the final per-image results are copied back.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "vpk_internal.cuh"
 
@@ -178,9 +181,23 @@ int vpk_pipeline_horizon(vpk_ctx* ctx, int32_t maxbest, double theta_vmin, doubl
 
 int vpk_pipeline_host(vpk_ctx* ctx, const double* segments, const int32_t* offsets, int32_t B, int32_t S, int32_t sphere_mode,
                       double alpha, const vpk_em_config* cfg, vpk_em_result* out, float* sigout, uint8_t* sphere_images) {
+    static const bool trace = getenv("VPK_PIPE_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     VPK_TRY(vpk_pipeline_upload(ctx, segments, offsets, B));
+    const auto t1 = std::chrono::steady_clock::now();
     VPK_TRY(vpk_pipeline_run(ctx, S, sphere_mode, alpha, cfg));
-    return vpk_pipeline_fetch(ctx, out, sigout, sphere_images);
+    const auto t2 = std::chrono::steady_clock::now();
+    const int rc = vpk_pipeline_fetch(ctx, out, sigout, sphere_images);
+    if (trace) {
+        const auto t3 = std::chrono::steady_clock::now();
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::milli>(b - a).count();
+        };
+        float dev[4] = {0, 0, 0, 0};
+        vpk_pipeline_stage_ms(ctx, dev);
+        fprintf(stderr, "[vpk_pipeline_host] upload %.3f ms, run %.3f ms (device %.3f), fetch %.3f ms\n", ms(t0, t1), ms(t1, t2), dev[3], ms(t2, t3));
+    }
+    return rc;
 }
 
 int vpk_pipeline_stage_ms(vpk_ctx* ctx, float ms[4]) {
