@@ -173,6 +173,20 @@ VPK_API int vpk_pipeline_fetch(vpk_ctx* ctx, vpk_em_result* out, float* sigout /
 VPK_API int vpk_pipeline_host(vpk_ctx* ctx, const double* segments, const int32_t* offsets, int32_t n_images,
                       int32_t size, int32_t sphere_mode, double alpha, const vpk_em_config* cfg,
                       vpk_em_result* out, float* sigout, uint8_t* sphere_images);
+/* ---- N2: raw LSD output -> normalised segments (+ lines) ---------------------- */
+/* The normalisation evaluation.detect_lsd_lines applies to lsd.detect_line_segments' rows (reference
+ * evaluation.py:227-251) and the line construction of evaluation.py:158-168, for a ragged batch on the
+ * device.  lsd: (sum N, ncols) float64 rows x1, y1, x2, y2, [width, p, -log10 NFA] in pixels
+ * (ncols >= 4; 7 for LSD's own output); widths / heights: image sizes in pixels.  segments_out (sum N, 4):
+ * origin at the image centre, divided by max(w, h) / 2, y up -- bit-identical to the numpy expressions;
+ * lines_out (sum N, 3) = [x1,y1,1] x [x2,y2,1] or NULL; nfa_out (sum N) = column 6 or NULL. */
+VPK_API int vpk_segments_from_lsd(vpk_ctx* ctx, const double* lsd, int32_t ncols, const int32_t* offsets, const int32_t* widths,
+                                  const int32_t* heights, int32_t n_images, double* segments_out, double* lines_out,
+                                  double* nfa_out);
+/* vpk_pipeline_upload for raw LSD rows: they are normalised on the device into the resident batch. */
+VPK_API int vpk_pipeline_upload_lsd(vpk_ctx* ctx, const double* lsd, int32_t ncols, const int32_t* offsets,
+                                    const int32_t* widths, const int32_t* heights, int32_t n_images);
+
 /* ---- N1: horizon line and orthogonal VP triplet --------------------------- */
 /* calc_horizon.calculate_horizon_and_ortho_vp(em_result, maxbest=10, theta_vmin=pi/10, theta_z=pi/4)
  * (reference calc_horizon.py:19-225; callers example.py:65, benchmark.py:233) for a batch of EM

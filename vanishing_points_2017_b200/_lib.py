@@ -21,6 +21,7 @@ SYMBOLS = [
     "vpk_profile_enable", "vpk_profile_reset", "vpk_profile_read", "vpk_lines_from_segments", "vpk_sphere_map",
     "vpk_cnn_load", "vpk_cnn_forward", "vpk_debug_gemm", "vpk_em_default_config", "vpk_em", "vpk_em_stats", "vpk_pipeline_upload", "vpk_pipeline_run",
     "vpk_pipeline_fetch", "vpk_pipeline_host", "vpk_pipeline_stage_ms", "vpk_horizon", "vpk_pipeline_horizon",
+    "vpk_segments_from_lsd", "vpk_pipeline_upload_lsd",
 ]
 
 
@@ -88,6 +89,9 @@ def load():
         lib.vpk_pipeline_stage_ms.argtypes = [C.c_void_p, C.c_void_p]
         lib.vpk_horizon.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double,
                                     C.c_void_p, C.c_void_p]
+        lib.vpk_segments_from_lsd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                              C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.vpk_pipeline_upload_lsd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         lib.vpk_pipeline_horizon.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
         _lib = lib
         return lib

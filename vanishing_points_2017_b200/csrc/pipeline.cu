@@ -63,6 +63,39 @@ int vpk_pipeline_upload(vpk_ctx* ctx, const double* segments, const int32_t* off
     return VPK_OK;
 }
 
+int vpk_pipeline_upload_lsd(vpk_ctx* ctx, const double* lsd, int32_t ncols, const int32_t* offsets, const int32_t* widths,
+                            const int32_t* heights, int32_t B) {
+    if (!ctx || !offsets || !widths || !heights || B <= 0 || ncols < 4 || offsets[0] != 0) { set_error("vpk_pipeline_upload_lsd: bad argument"); return VPK_ERR_ARG; }
+    for (int b = 0; b < B; ++b)
+        if (offsets[b + 1] < offsets[b] || widths[b] <= 0 || heights[b] <= 0) { set_error("vpk_pipeline_upload_lsd: bad offsets or image size"); return VPK_ERR_ARG; }
+    const int64_t sumN = offsets[B];
+    if (sumN > 0 && !lsd) { set_error("vpk_pipeline_upload_lsd: lsd is NULL"); return VPK_ERR_ARG; }
+    VPK_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->pipe) {
+        ctx->pipe = new PipeState();
+        for (auto& e : ctx->pipe->ev) VPK_CUDA(cudaEventCreate(&e));
+    }
+    PipeState* p = ctx->pipe;
+    p->B = B; p->sumN = sumN; p->have_result = false;
+    p->h_offsets.assign(offsets, offsets + B + 1);
+    VPK_TRY(p->seg.ensure((sumN + 1) * 4 * sizeof(double)));
+    VPK_TRY(p->lines.ensure((sumN + 1) * 3 * sizeof(double)));
+    VPK_TRY(p->offsets.ensure((size_t)(3 * (B + 1)) * sizeof(int32_t)));
+    VPK_TRY(ctx->d_misc.ensure((size_t)(sumN + 1) * ncols * sizeof(double)));
+    int32_t* d_off = p->offsets.as<int32_t>();
+    int32_t* d_w = d_off + (B + 1);
+    int32_t* d_h = d_w + (B + 1);
+    cudaStream_t st = ctx->stream;
+    if (sumN) VPK_CUDA(cudaMemcpyAsync(ctx->d_misc.p, lsd, (size_t)sumN * ncols * sizeof(double), cudaMemcpyHostToDevice, st));
+    VPK_CUDA(cudaMemcpyAsync(d_off, offsets, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    VPK_CUDA(cudaMemcpyAsync(d_w, widths, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    VPK_CUDA(cudaMemcpyAsync(d_h, heights, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    // the raw LSD rows are normalised where they land: no host loop, no second staging of segments
+    VPK_TRY(segments_from_lsd_dev(ctx, ctx->d_misc.as<double>(), ncols, d_off, d_w, d_h, B, sumN, p->seg.as<double>(), nullptr));
+    VPK_CUDA(cudaStreamSynchronize(st));
+    return VPK_OK;
+}
+
 int vpk_pipeline_run(vpk_ctx* ctx, int32_t S, int32_t sphere_mode, double alpha, const vpk_em_config* cfg_in) {
     if (!ctx || !ctx->pipe || ctx->pipe->B <= 0) { set_error("vpk_pipeline_run: no batch uploaded"); return VPK_ERR_STATE; }
     if (S != VPK_CNN_SIZE) { set_error("vpk_pipeline_run: the CNN input is %dx%d (cnn/deploy.prototxt:7); size=%d", VPK_CNN_SIZE, VPK_CNN_SIZE, S); return VPK_ERR_ARG; }

@@ -45,6 +45,41 @@ int lines_from_segments_dev(vpk_ctx* ctx, const double* d_seg, int64_t n, double
     return check_launch("lines_from_segments");
 }
 
+// Row N2 of SURVEY.md section 8(f): the normalisation of the raw LSD output that evaluation.detect_lsd_lines
+// applies (reference evaluation.py:240-249): pixel coordinates -> origin at the image centre, divided by
+// max(width, height) / 2, y pointing up; column 6 of the LSD rows (-log10 NFA) is passed through (:251).
+// Every operation is a single correctly rounded float64 operation in the reference's order, so the
+// result is bit-identical to numpy's.  One thread per segment; the image of a segment is found by
+// bisection over the offsets.
+__global__ void segments_from_lsd_kernel(const double* __restrict__ lsd, int ncols, const int32_t* __restrict__ offsets,
+                                         const int32_t* __restrict__ widths, const int32_t* __restrict__ heights, int B, int64_t n,
+                                         double* __restrict__ seg, double* __restrict__ nfa) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lo = 0, hi = B - 1;
+    while (lo < hi) {                               // last image with offsets[b] <= i
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int64_t)offsets[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    const double w = (double)widths[lo], h = (double)heights[lo];
+    const double half_w = __ddiv_rn(w, 2.0), half_h = __ddiv_rn(h, 2.0);
+    const double half_s = __ddiv_rn(fmax(w, h), 2.0);          // scale_w = scale_h = max(width, height) (:233-234)
+    const double* r = lsd + i * ncols;
+    const double x1 = __ddiv_rn(__dsub_rn(r[0], half_w), half_s), y1 = __ddiv_rn(__dsub_rn(r[1], half_h), half_s);
+    const double x2 = __ddiv_rn(__dsub_rn(r[2], half_w), half_s), y2 = __ddiv_rn(__dsub_rn(r[3], half_h), half_s);
+    seg[4 * i] = x1; seg[4 * i + 1] = __dmul_rn(y1, -1.0); seg[4 * i + 2] = x2; seg[4 * i + 3] = __dmul_rn(y2, -1.0);
+    if (nfa) nfa[i] = ncols > 6 ? r[6] : 0.0;
+}
+
+int segments_from_lsd_dev(vpk_ctx* ctx, const double* d_lsd, int ncols, const int32_t* d_offsets, const int32_t* d_widths,
+                          const int32_t* d_heights, int B, int64_t n, double* d_seg, double* d_nfa) {
+    if (n <= 0) return VPK_OK;
+    KernelScope ks(ctx, "segments_from_lsd");
+    segments_from_lsd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_lsd, ncols, d_offsets, d_widths, d_heights, B, n,
+                                                                                 d_seg, d_nfa);
+    return check_launch("segments_from_lsd");
+}
+
 // ---------------------------------------------------------------------------
 // shared index maps
 // ---------------------------------------------------------------------------
@@ -423,6 +458,43 @@ int vpk_lines_from_segments(vpk_ctx* ctx, const double* segments, int64_t n, dou
     VPK_TRY(lines_from_segments_dev(ctx, ctx->d_segments.as<double>(), n, ctx->d_lines.as<double>()));
     VPK_CUDA(cudaMemcpyAsync(lines_out, ctx->d_lines.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     VPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VPK_OK;
+}
+
+int vpk_segments_from_lsd(vpk_ctx* ctx, const double* lsd, int32_t ncols, const int32_t* offsets, const int32_t* widths,
+                          const int32_t* heights, int32_t B, double* segments_out, double* lines_out, double* nfa_out) {
+    if (!ctx || !offsets || !widths || !heights || B < 0 || ncols < 4 || !segments_out) { set_error("vpk_segments_from_lsd: bad argument"); return VPK_ERR_ARG; }
+    if (B == 0) return VPK_OK;
+    if (offsets[0] != 0) { set_error("vpk_segments_from_lsd: offsets[0] must be 0"); return VPK_ERR_ARG; }
+    for (int b = 0; b < B; ++b)
+        if (offsets[b + 1] < offsets[b] || widths[b] <= 0 || heights[b] <= 0) { set_error("vpk_segments_from_lsd: bad offsets or image size"); return VPK_ERR_ARG; }
+    const int64_t n = offsets[B];
+    if (n == 0) return VPK_OK;
+    if (!lsd) { set_error("vpk_segments_from_lsd: lsd is NULL"); return VPK_ERR_ARG; }
+    if (nfa_out && ncols < 7) { set_error("vpk_segments_from_lsd: the NFA column needs 7-column LSD rows"); return VPK_ERR_ARG; }
+    VPK_CUDA(cudaSetDevice(ctx->device));
+    VPK_TRY(ctx->d_misc.ensure((size_t)n * ncols * sizeof(double)));
+    VPK_TRY(ctx->d_segments.ensure((n + 1) * 4 * sizeof(double)));
+    VPK_TRY(ctx->d_lines.ensure((n + 1) * 3 * sizeof(double)));
+    VPK_TRY(ctx->d_offsets.ensure((size_t)(3 * (B + 1)) * sizeof(int32_t)));
+    VPK_TRY(ctx->d_weights.ensure((size_t)(n + 1) * sizeof(double)));
+    int32_t* d_off = ctx->d_offsets.as<int32_t>();
+    int32_t* d_w = d_off + (B + 1);
+    int32_t* d_h = d_w + (B + 1);
+    cudaStream_t st = ctx->stream;
+    VPK_CUDA(cudaMemcpyAsync(ctx->d_misc.p, lsd, (size_t)n * ncols * sizeof(double), cudaMemcpyHostToDevice, st));
+    VPK_CUDA(cudaMemcpyAsync(d_off, offsets, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    VPK_CUDA(cudaMemcpyAsync(d_w, widths, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    VPK_CUDA(cudaMemcpyAsync(d_h, heights, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    VPK_TRY(segments_from_lsd_dev(ctx, ctx->d_misc.as<double>(), ncols, d_off, d_w, d_h, B, n, ctx->d_segments.as<double>(),
+                                  nfa_out ? ctx->d_weights.as<double>() : nullptr));
+    VPK_CUDA(cudaMemcpyAsync(segments_out, ctx->d_segments.p, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (lines_out) {
+        VPK_TRY(lines_from_segments_dev(ctx, ctx->d_segments.as<double>(), n, ctx->d_lines.as<double>()));
+        VPK_CUDA(cudaMemcpyAsync(lines_out, ctx->d_lines.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    if (nfa_out) VPK_CUDA(cudaMemcpyAsync(nfa_out, ctx->d_weights.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    VPK_CUDA(cudaStreamSynchronize(st));
     return VPK_OK;
 }
 

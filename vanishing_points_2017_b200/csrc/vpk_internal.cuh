@@ -186,6 +186,9 @@ int em_dev(vpk_ctx* ctx, const double* d_lines, const double* d_segments, const 
            const vpk_em_config* cfg, const EmDeviceOut& out, int phase = 0);
 enum { EM_ALL = 0, EM_EARLY = 1 };
 
+int segments_from_lsd_dev(vpk_ctx* ctx, const double* d_lsd, int ncols, const int32_t* d_offsets, const int32_t* d_widths,
+                          const int32_t* d_heights, int B, int64_t n, double* d_seg, double* d_nfa);
+
 // horizon.cu: calc_horizon.calculate_horizon_and_ortho_vp for a batch of EM results on the device
 int horizon_dev(vpk_ctx* ctx, const double* d_vp, const int32_t* d_counts, const int32_t* d_n_vp, int32_t B, int32_t maxbest,
                 double theta_vmin, double theta_z, void* d_out);

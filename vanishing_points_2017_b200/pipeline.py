@@ -44,6 +44,19 @@ class Pipeline:
         _lib.check(self.ctx.lib.vpk_pipeline_upload(self.ctx.h, _lib.ptr(seg), _lib.ptr(off), self._B),
                    "vpk_pipeline_upload")
 
+    def upload_lsd(self, lsd_rows, offsets, widths, heights):
+        """upload() for raw LSD rows (flat (sum N, ncols) array, pixels): normalised on the device
+        (evaluation.py:240-249) into the resident batch."""
+        lsd = np.ascontiguousarray(lsd_rows, dtype=np.float64)
+        off = _lib.as_offsets(offsets)
+        if lsd.ndim != 2 or off[-1] != lsd.shape[0]:
+            raise ValueError("lsd_rows must be (sum N, ncols) with offsets[-1] == sum N")
+        w = np.ascontiguousarray(widths, dtype=np.int32)
+        h = np.ascontiguousarray(heights, dtype=np.int32)
+        self._B, self._off = off.size - 1, off
+        _lib.check(self.ctx.lib.vpk_pipeline_upload_lsd(self.ctx.h, _lib.ptr(lsd), lsd.shape[1], _lib.ptr(off), _lib.ptr(w),
+                                                        _lib.ptr(h), self._B), "vpk_pipeline_upload_lsd")
+
     def run(self):
         _lib.check(self.ctx.lib.vpk_pipeline_run(self.ctx.h, self.size, self.mode, self.alpha, C.byref(self.cfg)),
                    "vpk_pipeline_run")
