@@ -35,3 +35,53 @@ def segments_from_lsd(lsd_lines, image_shape):
     """What detect_lsd_lines returns for one image (evaluation.py:251): {'segments': (N,4), 'nfa': (N,)}."""
     out = segments_from_lsd_batch([lsd_lines], [image_shape], want_lines=False)
     return {"segments": out["segments"], "nfa": out["nfa"]}
+
+
+# ---------------------------------------------------------------------------------------------------
+# Row N3: the stage hand-off.  The reference passes one pickle per image from stage to stage
+# (evaluation.py:152-183 writes {'lines': datum, 'sphere_image'}, :283-289 adds 'cnn_prediction',
+# :344-349 adds 'EM_result'); the pipeline keeps everything in HBM instead.  For the reference's own
+# consumers (example.py:62-65, benchmark.py:228-241, result_plotting) the same dicts can be exported.
+# ---------------------------------------------------------------------------------------------------
+def reference_data(results, segments, offsets, sphere_images, cnn_predictions, image_shapes=None, images=None,
+                   extra=None):
+    """One dict per image with the layout of the reference's per-image pickle after run_em
+    (evaluation.py:349): {'lines': {'image_shape', 'image', 'line_segments', 'lines', ...},
+    'sphere_image' (S,S) uint8, 'cnn_prediction' (20,20) float32, 'EM_result' dict | None}.
+
+    'lines'['lines'] holds the ROW-NORMALISED homogeneous lines: the reference's EM normalises the array it
+    is given in place (vp_localisation.py:186, :226) and run_em_single stores that very array back
+    (evaluation.py:350).  A failed image gets the reference's skeleton dict with None entries
+    (vp_localisation.py:205-206); `status` is dropped (not a key of the reference)."""
+    seg = np.asarray(segments, np.float64).reshape(-1, 4)
+    off = np.asarray(offsets).astype(np.int64)
+    B = off.size - 1
+    out = []
+    for b in range(B):
+        s = seg[off[b]:off[b + 1]].copy()
+        p1 = np.concatenate([s[:, 0:2], np.ones((s.shape[0], 1))], axis=1)
+        p2 = np.concatenate([s[:, 2:4], np.ones((s.shape[0], 1))], axis=1)
+        lines = np.cross(p1, p2)                                              # evaluation.py:161-168
+        em = None
+        if results[b] is not None:
+            em = {k: v for k, v in results[b].items() if k != "status"}
+            em.setdefault("distribution", None)
+            if lines.shape[0]:
+                lines = lines / np.sqrt(np.sum(lines * lines, axis=1))[:, None]  # the EM's in-place normalisation
+        datum = {"image_shape": None if image_shapes is None else tuple(image_shapes[b]),
+                 "image": None if images is None else images[b], "line_segments": s, "lines": lines}
+        if extra is not None:
+            datum.update(extra[b])                                            # e.g. 'dataset', 'image_file' (:152)
+        out.append({"lines": datum, "sphere_image": None if sphere_images is None else np.asarray(sphere_images[b]),
+                    "cnn_prediction": None if cnn_predictions is None else np.asarray(cnn_predictions[b], np.float32),
+                    "EM_result": em})
+    return out
+
+
+def dump_reference_pickles(data, paths):
+    """Write the dicts of reference_data() as the reference writes them (evaluation.py:182-183:
+    pickle.dump(..., -1) under Python 2, i.e. protocol 2, which Python 2 and 3 both read)."""
+    import pickle
+    for d, p in zip(data, paths):
+        with open(p, "wb") as fh:
+            pickle.dump(d, fh, 2)
