@@ -194,13 +194,19 @@ VPK_API int vpk_pipeline_upload_lsd(vpk_ctx* ctx, const double* lsd, int32_t nco
  * out as vpk_em writes them (an image without VPs has n_vp = 0 and gets the reference's default
  * horizon, calc_horizon.py:207-212).  points (B, 5, 3) float64 receives the reference's return
  * values hP1, hP2, zVP, hVP1, hVP2 in that order; best_combo (B, 3) int32 the indices of the chosen
- * VPs (two entries and -1 when fewer than three VPs take part). */
+ * VPs (two entries and -1 when fewer than three VPs take part).
+ * Optional (row N4, the evaluation of benchmark.py:247-253): with true_horizons (B,3) homogeneous
+ * ground-truth horizon lines, scales (B) and heights (B) (benchmark.py's `scale` and `imageHeight`),
+ * errors (B) receives max(|hP1.y - thP1.y|, |hP2.y - thP2.y|) / 2 * scale / imageHeight; all four NULL
+ * otherwise. */
 VPK_API int vpk_horizon(vpk_ctx* ctx, const double* vp, const int32_t* counts, const int32_t* n_vp, int32_t n_images,
-                        int32_t maxbest, double theta_vmin, double theta_z, double* points, int32_t* best_combo);
+                        int32_t maxbest, double theta_vmin, double theta_z, const double* true_horizons,
+                        const double* scales, const double* heights, double* points, int32_t* best_combo, double* errors);
 /* The same on the device-resident EM result of the last vpk_pipeline_run (no host round trip of the
  * EM result; only the 5 points + 3 indices per image come back). */
-VPK_API int vpk_pipeline_horizon(vpk_ctx* ctx, int32_t maxbest, double theta_vmin, double theta_z, double* points,
-                                 int32_t* best_combo);
+VPK_API int vpk_pipeline_horizon(vpk_ctx* ctx, int32_t maxbest, double theta_vmin, double theta_z,
+                                 const double* true_horizons, const double* scales, const double* heights, double* points,
+                                 int32_t* best_combo, double* errors);
 
 /* device time of the last vpk_pipeline_run per stage: [lines+sphere, cnn, em, total] ms */
 VPK_API int vpk_pipeline_stage_ms(vpk_ctx* ctx, float ms[4]);

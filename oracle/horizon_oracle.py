@@ -99,3 +99,10 @@ def calculate_horizon_and_ortho_vp(em_result, maxbest=10, theta_vmin=np.pi / 10.
             hl = np.cross(np.array([0.0, 0.0, 1.0]), np.array([1.0, 0.0, 1.0]))
     hP1, hP2 = _horizon_points(np.asarray(hl, np.float64))
     return hP1, hP2, np.asarray(z, np.float64), np.asarray(hVP1, np.float64), np.asarray(hVP2, np.float64), np.asarray(combo)
+
+
+def horizon_error(hP1, hP2, true_horizon, scale, image_height):
+    """benchmark.py:247-253: distance of the estimated horizon from the ground truth at the image borders."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        thP1, thP2 = _horizon_points(np.asarray(true_horizon, np.float64))
+    return np.maximum(np.abs(hP1[1] - thP1[1]), np.abs(hP2[1] - thP2[1])) / 2 * scale * 1.0 / image_height

@@ -39,16 +39,31 @@ def _unpack(points, combo, n_vp, maxbest):
     return out
 
 
-def calculate_horizon_and_ortho_vp_batch(em_results, maxbest=10, theta_vmin=np.pi / 10., theta_z=np.pi / 4., ctx=None):
-    """One (hP1, hP2, zVP, hVP1, hVP2, best_combo) tuple per EM result dict."""
+def _truth(true_horizons, scales, image_heights, B):
+    """(B,3) ground-truth horizons, benchmark.py's `scale` and `imageHeight` per image -> contiguous float64."""
+    if true_horizons is None:
+        return None, None, None, None
+    th = np.ascontiguousarray(true_horizons, np.float64).reshape(B, 3)
+    sc = np.ascontiguousarray(np.broadcast_to(np.asarray(scales, np.float64), (B,)))
+    hh = np.ascontiguousarray(np.broadcast_to(np.asarray(image_heights, np.float64), (B,)))
+    return th, sc, hh, np.empty(B, np.float64)
+
+
+def calculate_horizon_and_ortho_vp_batch(em_results, maxbest=10, theta_vmin=np.pi / 10., theta_z=np.pi / 4., ctx=None,
+                                         true_horizons=None, scales=None, image_heights=None):
+    """One (hP1, hP2, zVP, hVP1, hVP2, best_combo) tuple per EM result dict.  With ground-truth horizons
+    (homogeneous lines), `scales` and `image_heights` as in benchmark.py:247-253, returns (tuples, errors)."""
     ctx = ctx or _lib.default_context()
     vp, counts, n_vp = _pack(em_results)
     B = len(em_results)
     points = np.empty((B, 5, 3), np.float64)
     combo = np.empty((B, 3), np.int32)
+    th, sc, hh, err = _truth(true_horizons, scales, image_heights, B)
     _lib.check(ctx.lib.vpk_horizon(ctx.h, _lib.ptr(vp), _lib.ptr(counts), _lib.ptr(n_vp), B, int(maxbest), float(theta_vmin),
-                                   float(theta_z), _lib.ptr(points), _lib.ptr(combo)), "vpk_horizon")
-    return _unpack(points, combo, n_vp, maxbest)
+                                   float(theta_z), _lib.ptr(th), _lib.ptr(sc), _lib.ptr(hh), _lib.ptr(points), _lib.ptr(combo),
+                                   _lib.ptr(err)), "vpk_horizon")
+    out = _unpack(points, combo, n_vp, maxbest)
+    return out if err is None else (out, err)
 
 
 def calculate_horizon_and_ortho_vp(em_result, maxbest=10, theta_vmin=np.pi / 10., theta_z=np.pi / 4.):

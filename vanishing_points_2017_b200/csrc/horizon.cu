@@ -18,7 +18,7 @@ namespace vpk {
 static constexpr int kHorizonThreads = 128;
 static constexpr int kHMax = VPK_MAX_VP;
 
-struct HorizonOut { double hP1[3], hP2[3], zVP[3], hVP1[3], hVP2[3]; int combo[3]; };
+struct HorizonOut { double hP1[3], hP2[3], zVP[3], hVP1[3], hVP2[3], err; int combo[3]; };
 
 struct Triplet {
     double score;
@@ -103,7 +103,9 @@ __device__ __forceinline__ void unrank_triplet(int idx, int n, int& a, int& b, i
 
 __global__ void __launch_bounds__(kHorizonThreads) horizon_kernel(const double* __restrict__ vp, const int32_t* __restrict__ counts,
                                                                   const int32_t* __restrict__ n_vp, int maxbest, double costh,
-                                                                  double sin_tz, HorizonOut* __restrict__ out) {
+                                                                  double sin_tz, const double* __restrict__ true_h,
+                                                                  const double* __restrict__ scales, const double* __restrict__ heights,
+                                                                  HorizonOut* __restrict__ out) {
     __shared__ double s_vp[kHMax][3];
     __shared__ int s_cnt[kHMax], s_best[kHMax];
     __shared__ unsigned char s_zen[kHMax];
@@ -180,28 +182,50 @@ __global__ void __launch_bounds__(kHorizonThreads) horizon_kernel(const double* 
     }
     horizon_point(hlin, 1.0, o.hP1);                                       // :219-222
     horizon_point(hlin, -1.0, o.hP2);
+    // horizon error against the ground-truth horizon (benchmark.py:247-253), NaN without one
+    o.err = nan("");
+    if (true_h) {
+        double t1[3], t2[3];
+        horizon_point(true_h + 3 * (size_t)img, 1.0, t1);
+        horizon_point(true_h + 3 * (size_t)img, -1.0, t2);
+        o.err = fmax(fabs(o.hP1[1] - t1[1]), fabs(o.hP2[1] - t2[1])) / 2 * scales[img] * 1.0 / heights[img];
+    }
     out[img] = o;
 }
 
 int horizon_dev(vpk_ctx* ctx, const double* d_vp, const int32_t* d_counts, const int32_t* d_n_vp, int32_t B, int32_t maxbest,
-                double theta_vmin, double theta_z, void* d_out) {
+                double theta_vmin, double theta_z, const double* d_truth, void* d_out) {
     if (B <= 0) return VPK_OK;
     KernelScope ks(ctx, "horizon");
-    horizon_kernel<<<B, kHorizonThreads, 0, ctx->stream>>>(d_vp, d_counts, d_n_vp, maxbest, cos(theta_vmin), sin(theta_z),
+    // d_truth: nullptr or (B,3) true horizons | (B) scales | (B) image heights, contiguous
+    horizon_kernel<<<B, kHorizonThreads, 0, ctx->stream>>>(d_vp, d_counts, d_n_vp, maxbest, cos(theta_vmin), sin(theta_z), d_truth,
+                                                          d_truth ? d_truth + 3 * (size_t)B : nullptr,
+                                                          d_truth ? d_truth + 4 * (size_t)B : nullptr,
                                                           static_cast<HorizonOut*>(d_out));
     return check_launch("horizon");
 }
 
 size_t horizon_out_bytes(int32_t B) { return sizeof(HorizonOut) * (size_t)B; }
 
+// (B,3) true horizons | (B) scales | (B) heights -> one device block
+int horizon_upload_truth(vpk_ctx* ctx, DBuf& buf, const double* true_horizons, const double* scales, const double* heights, int32_t B) {
+    VPK_TRY(buf.ensure(5 * (size_t)B * sizeof(double)));
+    double* d = buf.as<double>();
+    VPK_CUDA(cudaMemcpyAsync(d, true_horizons, 3 * (size_t)B * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    VPK_CUDA(cudaMemcpyAsync(d + 3 * (size_t)B, scales, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    VPK_CUDA(cudaMemcpyAsync(d + 4 * (size_t)B, heights, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return VPK_OK;
+}
+
 // unpack HorizonOut records (host copy) into the caller's arrays
-void horizon_unpack(const void* h_rec, int32_t B, double* points, int32_t* best_combo) {
+void horizon_unpack(const void* h_rec, int32_t B, double* points, int32_t* best_combo, double* errors) {
     const HorizonOut* r = static_cast<const HorizonOut*>(h_rec);
     for (int b = 0; b < B; ++b) {
         const double* src[5] = {r[b].hP1, r[b].hP2, r[b].zVP, r[b].hVP1, r[b].hVP2};
         for (int q = 0; q < 5; ++q)
             for (int k = 0; k < 3; ++k) points[((size_t)b * 5 + q) * 3 + k] = src[q][k];
         for (int k = 0; k < 3; ++k) best_combo[(size_t)b * 3 + k] = r[b].combo[k];
+        if (errors) errors[b] = r[b].err;
     }
 }
 
@@ -212,15 +236,17 @@ using namespace vpk;
 extern "C" {
 
 int vpk_horizon(vpk_ctx* ctx, const double* vp, const int32_t* counts, const int32_t* n_vp, int32_t n_images, int32_t maxbest,
-                double theta_vmin, double theta_z, double* points, int32_t* best_combo) {
-    if (!ctx || n_images < 0 || maxbest < 0 || (n_images > 0 && (!vp || !counts || !n_vp || !points || !best_combo))) {
+                double theta_vmin, double theta_z, const double* true_horizons, const double* scales, const double* heights,
+                double* points, int32_t* best_combo, double* errors) {
+    if (!ctx || n_images < 0 || maxbest < 0 || (n_images > 0 && (!vp || !counts || !n_vp || !points || !best_combo)) ||
+        (errors && !(true_horizons && scales && heights))) {
         set_error("vpk_horizon: bad argument");
         return VPK_ERR_ARG;
     }
     if (n_images == 0) return VPK_OK;
     VPK_CUDA(cudaSetDevice(ctx->device));
     const size_t B = (size_t)n_images;
-    DBuf dvp, dc, dn, dout;
+    DBuf dvp, dc, dn, dout, dtruth;
     HBuf hout;
     int rc = VPK_OK;
     do {
@@ -230,13 +256,18 @@ int vpk_horizon(vpk_ctx* ctx, const double* vp, const int32_t* counts, const int
         cudaMemcpyAsync(dvp.p, vp, B * kHMax * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(dc.p, counts, B * kHMax * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(dn.p, n_vp, B * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
-        if ((rc = horizon_dev(ctx, dvp.as<double>(), dc.as<int32_t>(), dn.as<int32_t>(), n_images, maxbest, theta_vmin, theta_z, dout.p))) break;
+        const double* d_truth = nullptr;
+        if (errors) {
+            if ((rc = horizon_upload_truth(ctx, dtruth, true_horizons, scales, heights, n_images))) break;
+            d_truth = dtruth.as<double>();
+        }
+        if ((rc = horizon_dev(ctx, dvp.as<double>(), dc.as<int32_t>(), dn.as<int32_t>(), n_images, maxbest, theta_vmin, theta_z, d_truth, dout.p))) break;
         cudaMemcpyAsync(hout.p, dout.p, horizon_out_bytes(n_images), cudaMemcpyDeviceToHost, ctx->stream);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { set_error("vpk_horizon: %s", cudaGetErrorString(e)); rc = VPK_ERR_CUDA; break; }
-        horizon_unpack(hout.p, n_images, points, best_combo);
+        horizon_unpack(hout.p, n_images, points, best_combo, errors);
     } while (0);
-    dvp.release(); dc.release(); dn.release(); dout.release(); hout.release();
+    dvp.release(); dc.release(); dn.release(); dout.release(); dtruth.release(); hout.release();
     return rc;
 }
 

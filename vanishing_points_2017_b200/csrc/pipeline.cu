@@ -18,7 +18,7 @@ struct PipeState {
     int64_t sumN = 0;
     int S = 0;
     std::vector<int32_t> h_offsets;
-    DBuf seg, lines, offsets, hist, images, sigout, out_small, out_assoc, horizon;
+    DBuf seg, lines, offsets, hist, images, sigout, out_small, out_assoc, horizon, truth;
     HBuf h_horizon, h_small, h_assoc;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool have_result = false;
@@ -29,7 +29,7 @@ void pipe_free(vpk_ctx* ctx) {
     if (!ctx->pipe) return;
     PipeState* p = ctx->pipe;
     p->seg.release(); p->lines.release(); p->offsets.release(); p->hist.release(); p->images.release();
-    p->sigout.release(); p->out_small.release(); p->out_assoc.release(); p->horizon.release(); p->h_horizon.release(); p->h_small.release(); p->h_assoc.release();
+    p->sigout.release(); p->out_small.release(); p->out_assoc.release(); p->horizon.release(); p->truth.release(); p->h_horizon.release(); p->h_small.release(); p->h_assoc.release();
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     delete p;
     ctx->pipe = nullptr;
@@ -197,18 +197,24 @@ int vpk_pipeline_fetch(vpk_ctx* ctx, vpk_em_result* out, float* sigout, uint8_t*
     return VPK_OK;
 }
 
-int vpk_pipeline_horizon(vpk_ctx* ctx, int32_t maxbest, double theta_vmin, double theta_z, double* points, int32_t* best_combo) {
+int vpk_pipeline_horizon(vpk_ctx* ctx, int32_t maxbest, double theta_vmin, double theta_z, const double* true_horizons,
+                         const double* scales, const double* heights, double* points, int32_t* best_combo, double* errors) {
     if (!ctx || !ctx->pipe || !ctx->pipe->have_result) { set_error("vpk_pipeline_horizon: no completed run"); return VPK_ERR_STATE; }
-    if (!points || !best_combo || maxbest < 0) { set_error("vpk_pipeline_horizon: bad argument"); return VPK_ERR_ARG; }
+    if (!points || !best_combo || maxbest < 0 || (errors && !(true_horizons && scales && heights))) { set_error("vpk_pipeline_horizon: bad argument"); return VPK_ERR_ARG; }
     VPK_CUDA(cudaSetDevice(ctx->device));
     PipeState* p = ctx->pipe;
     VPK_TRY(p->horizon.ensure(horizon_out_bytes(p->B)));
     VPK_TRY(p->h_horizon.ensure(horizon_out_bytes(p->B)));
     // the EM result stays where the EM wrote it: no host round trip between the two
-    VPK_TRY(horizon_dev(ctx, p->out.vp, p->out.counts, p->out.n_vp, p->B, maxbest, theta_vmin, theta_z, p->horizon.p));
+    const double* d_truth = nullptr;
+    if (errors) {
+        VPK_TRY(horizon_upload_truth(ctx, p->truth, true_horizons, scales, heights, p->B));
+        d_truth = p->truth.as<double>();
+    }
+    VPK_TRY(horizon_dev(ctx, p->out.vp, p->out.counts, p->out.n_vp, p->B, maxbest, theta_vmin, theta_z, d_truth, p->horizon.p));
     VPK_CUDA(cudaMemcpyAsync(p->h_horizon.p, p->horizon.p, horizon_out_bytes(p->B), cudaMemcpyDeviceToHost, ctx->stream));
     VPK_CUDA(cudaStreamSynchronize(ctx->stream));
-    horizon_unpack(p->h_horizon.p, p->B, points, best_combo);
+    horizon_unpack(p->h_horizon.p, p->B, points, best_combo, errors);
     return VPK_OK;
 }
 

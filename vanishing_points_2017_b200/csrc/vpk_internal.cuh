@@ -191,9 +191,10 @@ int segments_from_lsd_dev(vpk_ctx* ctx, const double* d_lsd, int ncols, const in
 
 // horizon.cu: calc_horizon.calculate_horizon_and_ortho_vp for a batch of EM results on the device
 int horizon_dev(vpk_ctx* ctx, const double* d_vp, const int32_t* d_counts, const int32_t* d_n_vp, int32_t B, int32_t maxbest,
-                double theta_vmin, double theta_z, void* d_out);
+                double theta_vmin, double theta_z, const double* d_truth, void* d_out);
 size_t horizon_out_bytes(int32_t B);
-void horizon_unpack(const void* h_rec, int32_t B, double* points, int32_t* best_combo);
+int horizon_upload_truth(vpk_ctx* ctx, DBuf& buf, const double* true_horizons, const double* scales, const double* heights, int32_t B);
+void horizon_unpack(const void* h_rec, int32_t B, double* points, int32_t* best_combo, double* errors);
 
 void cnn_free(vpk_ctx* ctx);
 void em_free(vpk_ctx* ctx);

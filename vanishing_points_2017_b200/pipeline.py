@@ -70,16 +70,21 @@ class Pipeline:
         out = arrs if raw else unpack_results(arrs, self._off)
         return (out, sig, sph) if (want_response or want_sphere) else out
 
-    def horizons(self, maxbest=10, theta_vmin=np.pi / 10., theta_z=np.pi / 4.):
+    def horizons(self, maxbest=10, theta_vmin=np.pi / 10., theta_z=np.pi / 4., true_horizons=None, scales=None,
+                 image_heights=None):
         """calc_horizon.calculate_horizon_and_ortho_vp (calc_horizon.py:19-225) on the device-resident EM
-        result of the last run(): one (hP1, hP2, zVP, hVP1, hVP2, best_combo) tuple per image."""
+        result of the last run(): one (hP1, hP2, zVP, hVP1, hVP2, best_combo) tuple per image; with ground-truth
+        horizons also the horizon errors of benchmark.py:247-253 -> (tuples, errors)."""
         from . import calc_horizon
         points = np.empty((self._B, 5, 3), np.float64)
         combo = np.empty((self._B, 3), np.int32)
-        _lib.check(self.ctx.lib.vpk_pipeline_horizon(self.ctx.h, int(maxbest), float(theta_vmin), float(theta_z),
-                                                     _lib.ptr(points), _lib.ptr(combo)), "vpk_pipeline_horizon")
+        th, sc, hh, err = calc_horizon._truth(true_horizons, scales, image_heights, self._B)
+        _lib.check(self.ctx.lib.vpk_pipeline_horizon(self.ctx.h, int(maxbest), float(theta_vmin), float(theta_z), _lib.ptr(th),
+                                                     _lib.ptr(sc), _lib.ptr(hh), _lib.ptr(points), _lib.ptr(combo),
+                                                     _lib.ptr(err)), "vpk_pipeline_horizon")
         n_vp = np.array([3 if c[2] >= 0 else 0 for c in combo])
-        return calc_horizon._unpack(points, combo, n_vp, 3)
+        out = calc_horizon._unpack(points, combo, n_vp, 3)
+        return out if err is None else (out, err)
 
     def stage_ms(self):
         ms = (C.c_float * 4)()
