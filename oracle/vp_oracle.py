@@ -158,7 +158,10 @@ def find_initial_vps(sphere_image, resp, num_max):
     maxima = find_maxima(resp).flatten()
     flat = resp.flatten()
     idx = np.where(maxima == 1)[0]
-    order = np.argsort(flat[idx])[::-1]
+    # Equal responses (a saturated sigmoid gives exact float32 ties) are ordered by numpy.argsort's default
+    # sort in the reference (:123), i.e. by whatever the numpy build does with ties; the stable order is used
+    # here and in the kernel (csrc/em_core.cuh, init_prior_and_vps): of equal maxima the later cell wins.
+    order = np.argsort(flat[idx], kind="stable")[::-1]
     maxima[idx[order[num_max:]]] = 0
     maxima = maxima.reshape(resp.shape)
     vps = []

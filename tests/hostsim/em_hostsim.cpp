@@ -2,6 +2,7 @@
 // (vanishing_points_2017_b200/csrc/em_core.cuh, team = 1 thread) so that the
 // control flow the CUDA kernels run can be checked against the golden vectors on
 // a box without a GPU.  Never linked into libvpk.so, never imported by the package.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -45,6 +46,15 @@ extern "C" int hostsim_em(const double* lines, const double* segs, int N, const 
     } else {
         for (int n = 0; n < N; ++n) { im.lweight[n] = 1.0; im.colsum[n] = 0.0; }
     }
+#if defined(VPK_HOST_TRACE)
+    if (getenv("VPK_TRACE_LWEIGHT")) {
+        FILE* fh = fopen(getenv("VPK_TRACE_LWEIGHT"), "wb");
+        fwrite(im.lweight, sizeof(double), N, fh);
+        fwrite(im.colsum, sizeof(double), N, fh);
+        fwrite(im.lsim, sizeof(double), lsim_doubles(N), fh);
+        fclose(fh);
+    }
+#endif
     InitScratch* isc = new InitScratch();
     for (int c = 0; c < kCells; ++c) isc->resp[c] = resp[c];
     PostScratch* sc = new PostScratch();

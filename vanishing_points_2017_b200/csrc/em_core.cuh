@@ -16,6 +16,9 @@
 // merge decisions, choice of the next superstep).  `phase` says what POST does
 // with the fresh E/W results.
 #pragma once
+#if defined(VPK_HOST_TRACE)
+#include <cstdio>
+#endif
 #include <math.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -259,6 +262,14 @@ VPK_DEV double cos_clipped_multiple(double c, double f) {
     if (isnan(c)) dphi = c;
     return cos(fmin(fmax(f * dphi, -0.5 * kPi), 0.5 * kPi));
 }
+// lines_points_cosangle (:715-724), literally: no polynomial shortcut
+VPK_DEV double cosangle_reference_order(const Seg& a, const Seg& b, double f) {
+    double v1x = a.x1 - a.x2, v1y = a.y1 - a.y2, v2x = b.x1 - b.x2, v2y = b.y1 - b.y2;
+    double c = fabs((v1x * v2x + v1y * v2y) / (sqrt(v1x * v1x + v1y * v1y) * sqrt(v2x * v2x + v2y * v2y)));
+    double dphi = fabs(acos(fmin(fmax(c, -1.0), 1.0)));
+    if (isnan(c)) dphi = c;
+    return cos(fmin(fmax(f * dphi, -0.5 * kPi), 0.5 * kPi));
+}
 // lines_points_cosangle (:715-724)
 VPK_DEV double cosangle(const Seg& a, const Seg& b, double f) {
     double v1x = a.x1 - a.x2, v1y = a.y1 - a.y2, v2x = b.x1 - b.x2, v2y = b.y1 - b.y2;
@@ -323,7 +334,12 @@ VPK_DEVFN double rate_line(const double* lp, int i, const int* cj, const double*
     double c[kK1], px[kK1];
     for (int q = 0; q < cnt; ++q) {
         const SegPre sj = seg_pre(load_seg(lp, cj[q]));
-        double cc = cos9_pre(si, sj);
+        // The k2 neighbours are SELECTED by this value (:57-59) and real LSD output is full of exactly
+        // parallel segments, whose cosangles are equal up to the last bits: the value is computed with the
+        // reference's own expression and operation order (division by the product of the two norms, acos,
+        // cos; lines_points_cosangle :715-724), not with the reciprocal / Chebyshev form used for the N^2
+        // entries of the similarity matrix, so that near-ties fall the way they do in the reference.
+        double cc = cosangle_reference_order(load_seg(lp, i), load_seg(lp, cj[q]), 9.0);
         double d2true = (cj[q] == i) ? seg_distance2(si, sj) : cd2[q];     // :65 recomputes the true distance
         px[q] = prox_pre(si, sj, d2true);
         c[q] = isnan(cc) ? -INFINITY : cc;
@@ -646,6 +662,10 @@ VPK_DEVFN void init_prior_and_vps(EmSlot& st, InitScratch& sc, const uint8_t* im
                 ++M;
             }
         st.M = M;
+#if defined(VPK_HOST_TRACE)
+        printf("[trace] initial VPs M=%d\n", M);
+        for (int m = 0; m < M; ++m) printf("[trace]   %d: %.9f %.9f %.9f\n", m, st.cur[m][0], st.cur[m][1], st.cur[m][2]);
+#endif
     }
     team_sync();
 }
@@ -1568,6 +1588,9 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
         }
         case PH_HARD_REFIT: {
             argmax_assoc(im, st.M, T);
+#if defined(VPK_HOST_TRACE)
+            { int bc[kMaxM] = {0}; for (int n = 0; n < N; ++n) bc[im.assoc[n]]++; printf("[trace] HARD_REFIT M=%d assoc bincount:", st.M); for (int m = 0; m < st.M; ++m) printf(" %d", bc[m]); printf("\n"); }
+#endif
             // hard-assignment refit (:353-392)
             const int M2 = st.M;
             RefitAcc* acc = refit_acc(sc);
@@ -1592,6 +1615,9 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
                 }
                 sc.rem[m] = rem;
             }
+#if defined(VPK_HOST_TRACE)
+            printf("[trace] HARD_REFIT removed:"); for (int m = 0; m < M2; ++m) if (sc.rem[m]) printf(" %d", m); printf("  s:"); for (int m = 0; m < M2; ++m) printf(" %.6e", st.s[m]); printf("\n");
+#endif
             compact_vps(st, sc.rem, T);
             if (st.M == 0) {                                    // "decision metric is empty" (:400-404)
                 write_result(out, im, st, VPK_EM_NO_VPS_LEFT, 0, false, T);
@@ -1606,6 +1632,9 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
             for (int m = T.tid; m < st.M; m += T.nthreads) sc.rem[m] = 1;
             team_sync();
             for (int n = T.tid; n < N; n += T.nthreads) sc.rem[im.assoc[n]] = 0;
+#if defined(VPK_HOST_TRACE)
+            { int bc[kMaxM] = {0}; for (int n = 0; n < N; ++n) bc[im.assoc[n]]++; printf("[trace] KEEP_WINNERS M=%d bincount:", st.M); for (int m = 0; m < st.M; ++m) printf(" %d", bc[m]); printf("\n"); }
+#endif
             compact_vps(st, sc.rem, T);
             if (T.tid == 0) st.vidx = 0;
             request(st, 1, PH_FINAL_COUNTS, T, &sc);                 // :415 (index i+1)
@@ -1613,6 +1642,9 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
         }
         case PH_FINAL_COUNTS: {
             line_counts(im, st, cfg.outlier_thresh, T);
+#if defined(VPK_HOST_TRACE)
+            printf("[trace] FINAL_COUNTS M=%d counts:", st.M); for (int m = 0; m < st.M; ++m) printf(" %d", st.cnt[m]); printf("\n");
+#endif
             // drop VPs with too few lines, front to back (:423-437)
             if (T.tid == 0) {
                 int v = st.vidx;
