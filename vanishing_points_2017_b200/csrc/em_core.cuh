@@ -262,13 +262,25 @@ VPK_DEV double cos_clipped_multiple(double c, double f) {
     if (isnan(c)) dphi = c;
     return cos(fmin(fmax(f * dphi, -0.5 * kPi), 0.5 * kPi));
 }
-// lines_points_cosangle (:715-724), literally: no polynomial shortcut
+// lines_points_cosangle (:715-724), literally: no polynomial shortcut, and on the device every operation
+// individually rounded (nvcc would otherwise contract a*b + c*d into a fused multiply-add and move the
+// last bit of c, which is what decides near-ties)
 VPK_DEV double cosangle_reference_order(const Seg& a, const Seg& b, double f) {
     double v1x = a.x1 - a.x2, v1y = a.y1 - a.y2, v2x = b.x1 - b.x2, v2y = b.y1 - b.y2;
+#if defined(__CUDA_ARCH__)
+    const double dot = __dadd_rn(__dmul_rn(v1x, v2x), __dmul_rn(v1y, v2y));
+    const double n1 = __dsqrt_rn(__dadd_rn(__dmul_rn(v1x, v1x), __dmul_rn(v1y, v1y)));
+    const double n2 = __dsqrt_rn(__dadd_rn(__dmul_rn(v2x, v2x), __dmul_rn(v2y, v2y)));
+    double c = fabs(__ddiv_rn(dot, __dmul_rn(n1, n2)));
+    double dphi = fabs(acos(fmin(fmax(c, -1.0), 1.0)));
+    if (isnan(c)) dphi = c;
+    return cos(fmin(fmax(__dmul_rn(f, dphi), -0.5 * kPi), 0.5 * kPi));
+#else
     double c = fabs((v1x * v2x + v1y * v2y) / (sqrt(v1x * v1x + v1y * v1y) * sqrt(v2x * v2x + v2y * v2y)));
     double dphi = fabs(acos(fmin(fmax(c, -1.0), 1.0)));
     if (isnan(c)) dphi = c;
     return cos(fmin(fmax(f * dphi, -0.5 * kPi), 0.5 * kPi));
+#endif
 }
 // lines_points_cosangle (:715-724)
 VPK_DEV double cosangle(const Seg& a, const Seg& b, double f) {
