@@ -13,7 +13,7 @@
 //               W kernel streams contiguous memory), its column sums, and the
 //               kNN line rating (E4) from the same distances.
 //   em_init   : once per image: unit lines, prior mixture, initial VPs (E0-E2).
-//   superstep : em_estep (CTA = 128 lines of an image; E5) ->
+//   superstep : em_estep (CTA = 32 lines of an image; E5) ->
 //               em_wmat  (CTA = (image, slab): the (M x N)(N x N) weight-matrix
 //                         product E6, lsim streamed by bulk async copies through
 //                         a 4-stage shared-memory ring, FP64 FMA) ->
