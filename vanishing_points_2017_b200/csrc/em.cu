@@ -39,7 +39,7 @@ namespace vpk {
 
 using namespace em;
 
-static constexpr int kInitThreads = 256;
+static constexpr int kInitThreads = 512;
 static constexpr int kPairThreads = 256;
 static constexpr int kEThreads = 256;
 static constexpr int kWThreads = 256;
