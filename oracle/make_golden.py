@@ -55,6 +55,8 @@ def load_reference():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
+    ap.add_argument("--large", action="store_true",
+                    help="only the N = 1600 run (em_full_n1600_large.npz; the reference takes minutes there)")
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     warnings.simplefilter("ignore")
@@ -65,6 +67,9 @@ def main():
     vp, prob = load_reference()
     import contextlib, io
 
+    S = 500
+    if args.large:
+        return full_runs(vp, args.out, S, [("n1600_large", 301, 1600, 800, 600, "ideal", 0.15, 1, 1.0)])
     # ---- function-level vectors (one small scene) -------------------------
     sc = synth.make_scene(seed=11, n_segments=72, width=640, height=480)
     lp = sc["segments"]
@@ -133,7 +138,10 @@ def main():
     print("split: M 3 ->", sp["v"].shape[1])
 
     # ---- full EM runs ------------------------------------------------------
-    cases = [
+    full_runs(vp, args.out, S, FULL_CASES)
+
+
+FULL_CASES = [
         # (tag, seed, N, w, h, response kind, outlier_frac, extra_vps)
         ("n90_ideal", 101, 90, 640, 480, "ideal", 0.15, 0),
         ("n150_ideal", 102, 150, 640, 480, "ideal", 0.15, 0),
@@ -147,6 +155,12 @@ def main():
         ("n600_long", 204, 600, 800, 600, "ideal", 0.3, 2, 3.0),
         ("n800_long", 203, 800, 800, 600, "ideal", 0.15, 0, 1.0),
     ]
+
+
+def full_runs(vp, out_dir, S, cases):
+    import contextlib, io
+    from vanishing_points_2017_b200 import synth
+    from oracle import sphere_oracle
     split_calls = []
     orig_split = vp.split_best_vp
 
@@ -181,7 +195,7 @@ def main():
                                               distance_measure="angle", use_weights=True, do_split=True,
                                               do_merge=True)
         log = buf.getvalue()
-        np.savez_compressed(os.path.join(args.out, "em_full_%s.npz" % tag),
+        np.savez_compressed(os.path.join(out_dir, "em_full_%s.npz" % tag),
                             segments=lp, lines=lines, resp=resp, sphere_image=img, true_vps=sc["vps"],
                             vp=res["vp"], counts=res["counts"], counts_weighted=res["counts_weighted"],
                             vp_assoc=res["vp_assoc"], sigma=res["sigma"],
@@ -196,7 +210,7 @@ def main():
             llen = np.array([vp.line_length(x) for x in lp])
             with contextlib.redirect_stdout(io.StringIO()):
                 lwt = llen * np.clip(vp.line_rating_knn(lp, k2=4), 0.2, 1)
-            np.savez_compressed(os.path.join(args.out, "em_split_real_n600.npz"), lp=lp, l=ln, lweight=lwt,
+            np.savez_compressed(os.path.join(out_dir, "em_split_real_n600.npz"), lp=lp, l=ln, lweight=lwt,
                                 langles=vp.lines_angles(lp), **c)
             print("  split vector: M %d -> %d" % (c["v_in"].shape[0], c["v_out"].shape[0]))
 

@@ -18,6 +18,34 @@ def test_header_and_binding_agree():
     assert declared_symbols() == sorted(_lib.SYMBOLS)
 
 
+def declared_prototypes():
+    """name -> list of parameter declarations of every VPK_API prototype in include/vpk.h"""
+    text = re.sub(r"/\*.*?\*/", " ", open(os.path.join(ROOT, "include", "vpk.h")).read(), flags=re.S)
+    protos = {}
+    for name, params in re.findall(r"VPK_API\s+[\w\s\*]+?\b(vpk_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        params = " ".join(params.split())
+        protos[name] = [] if params in ("", "void") else [q.strip() for q in params.split(",")]
+    return protos
+
+
+def test_binding_declares_every_parameter_of_every_prototype():
+    """ctypes accepts undeclared extra arguments of a cdecl function (no conversion check); every binding must
+    therefore declare exactly the parameters of its prototype, pointers as pointers."""
+    lib = _lib.load()
+    protos = declared_prototypes()
+    assert sorted(protos) == sorted(_lib.SYMBOLS)
+    for name, params in protos.items():
+        at = getattr(lib, name).argtypes
+        assert at is not None, "%s: argtypes not declared" % name
+        assert len(at) == len(params), "%s: binding declares %d parameters, vpk.h %d" % (name, len(at), len(params))
+        for t, decl in zip(at, params):
+            is_ptr = "*" in decl or "[" in decl
+            ctypes_ptr = t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or issubclass(t, ctypes._Pointer)
+            assert is_ptr == ctypes_ptr, "%s: parameter %r bound as %r" % (name, decl, t)
+            if "double" in decl and not is_ptr:
+                assert t is ctypes.c_double, (name, decl)
+
+
 def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared_symbols():

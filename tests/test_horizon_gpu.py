@@ -50,7 +50,7 @@ def test_batch_equals_single_and_drop_in_signature():
 def test_pipeline_horizons_match_oracle_on_device_resident_em_result():
     from vanishing_points_2017_b200 import cnn as vcnn, pipeline
     ws, bs = vcnn.random_weights(0, scale=3.0)
-    pipe = pipeline.Pipeline(0, ws, bs)
+    pipe = pipeline.Pipeline(0, ws, bs, sphere_mode="votes")
     batch = synth.make_batch(2, n_images=6)
     res = pipe(batch["segments"], batch["offsets"])
     hz = pipe.horizons(maxbest=20)                                            # example.py:65 uses maxbest=20

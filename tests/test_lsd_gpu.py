@@ -34,7 +34,7 @@ def test_batch_is_bit_identical_to_the_reference():
 def test_pipeline_from_raw_lsd_rows_equals_pipeline_from_segments():
     from vanishing_points_2017_b200 import cnn as vcnn, pipeline
     ws, bs = vcnn.random_weights(0, scale=3.0)
-    pipe = pipeline.Pipeline(0, ws, bs)
+    pipe = pipeline.Pipeline(0, ws, bs, sphere_mode="votes")
     batch = synth.make_batch(2, n_images=5)
     seg, off = batch["segments"], batch["offsets"]
     # raw pixel rows that normalise to the batch's segments: invert evaluation.py:240-249 for 640x480 images

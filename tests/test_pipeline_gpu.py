@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 def pipe():
     from vanishing_points_2017_b200 import pipeline
     ws, bs = cnn_oracle.random_weights(0, scale=3.0)
-    return pipeline.Pipeline(0, ws, bs), ws, bs
+    return pipeline.Pipeline(0, ws, bs, sphere_mode="votes"), ws, bs
 
 
 def test_pipeline_matches_stagewise_oracles(pipe):

@@ -90,3 +90,33 @@ def test_full_size_properties(sm):
     r = sm.sphere_map_batch(batch["lines"], off, 500, "votes", want_image=False)
     n = np.diff(off).astype(np.int64)
     np.testing.assert_array_equal(r["hist"].reshape(len(n), -1).sum(axis=1), n * (n - 1) // 2)
+
+
+def test_votes_against_the_reference_projection_golden(sm, golden_dir):
+    """Directly against vectors of the reference's own coordinate_conversion.py (oracle/make_golden_sphere.py):
+    every one of the 101 025 pairwise intersections of a 450-line scene must land in the cell that
+    round(angle_to_index(point_to_angle(p))) gives (coordinate_conversion.py:23-35, 53-61)."""
+    import os
+    g = np.load(os.path.join(golden_dir, "sphere_cases.npz"))
+    want = np.bincount(g["votes_rows"].astype(np.int64) * 500 + g["votes_cols"], minlength=250000).reshape(500, 500)
+    hist, _ = sm.sphere_votes(g["votes_lines"], 500)
+    np.testing.assert_array_equal(hist.astype(np.int64), want)
+    # and from the segments (S0 + S1 on the device)
+    lines = sm.lines_from_segments(g["votes_segments"])
+    np.testing.assert_array_equal(lines, g["votes_lines"])
+
+
+def test_curves_cover_every_sample_of_the_reference_expression(sm, golden_dir):
+    """curves mode: every (row, column) sample of beta(alpha) as the reference's own expression
+    (sphere_mapping.py:40, 61-63) produces it must be a covered pixel of that line's raster."""
+    import os
+    g = np.load(os.path.join(golden_dir, "sphere_cases.npz"))
+    lines, rows = g["curves_lines"], g["curves_rows"].astype(np.int64)
+    a = g["curves_alpha"]
+    cols = np.clip(np.floor((a / np.pi + 0.5 - 0.5 / 500) * 500 + 0.5), 0, 499).astype(np.int64)
+    for i in range(0, lines.shape[0], 6):
+        r = sm.sphere_map_batch(lines[i:i + 1], [0, 1], 500, "curves")
+        cover = r["hist"][0]
+        ok = rows[i] >= 0
+        assert cover.max() == 1
+        assert np.all(cover[rows[i][ok], cols[ok]] == 1)

@@ -11,7 +11,7 @@ rows = [g["lsd_%d" % i] for i in range(n)]
 shapes = [tuple(int(v) for v in g["shape_%d" % i]) for i in range(n)]
 off = np.concatenate([[0], np.cumsum([r.shape[0] for r in rows])]).astype(np.int32)
 ws, bs = cnn_oracle.random_weights(0, scale=3.0)
-pipe = pipeline.Pipeline(0, ws, bs)
+pipe = pipeline.Pipeline(0, ws, bs, sphere_mode="votes")
 pipe.upload_lsd(np.concatenate(rows), off, [s[1] for s in shapes], [s[0] for s in shapes])
 pipe.run()
 res, sig, sph = pipe.fetch(want_response=True, want_sphere=True)

@@ -7,7 +7,7 @@ from oracle import cnn_oracle
 from vanishing_points_2017_b200 import pipeline, synth
 
 ws, bs = cnn_oracle.random_weights(0, scale=3.0)
-p = pipeline.Pipeline(0, ws, bs)
+p = pipeline.Pipeline(0, ws, bs, sphere_mode="votes")
 batch = synth.make_batch(2, n_images=5)
 res, sig, sph = p(batch["segments"], batch["offsets"], want_response=True, want_sphere=True)
 out = {"segments": batch["segments"], "offsets": batch["offsets"], "sig": sig, "sph": sph}

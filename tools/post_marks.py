@@ -10,7 +10,7 @@ from vanishing_points_2017_b200 import cnn as vcnn, pipeline  # noqa: E402
 cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 name, seg, off = bench.make_workload(cfg, 0, None)
 ws, bs = vcnn.random_weights(0)
-pipe = pipeline.Pipeline(0, ws, bs)
+pipe = pipeline.Pipeline(0, ws, bs, sphere_mode="votes")
 pipe.upload(seg, off)
 pipe.run()
 pipe.ctx.profile_enable(True)

@@ -14,7 +14,7 @@ ap.add_argument("--runs", type=int, default=1)
 a = ap.parse_args()
 name, seg, off = bench.make_workload(a.config, 0, a.images)
 ws, bs = vcnn.random_weights(0)
-pipe = pipeline.Pipeline(0, ws, bs)
+pipe = pipeline.Pipeline(0, ws, bs, sphere_mode="votes")
 pipe.upload(seg, off)
 for _ in range(a.runs):
     pipe.run()

@@ -3,7 +3,7 @@ sys.path.insert(0, "/root/repo")
 from oracle import cnn_oracle, sphere_oracle, vp_oracle
 from vanishing_points_2017_b200 import pipeline, synth
 ws, bs = cnn_oracle.random_weights(0, scale=3.0)
-pipe = pipeline.Pipeline(0, ws, bs)
+pipe = pipeline.Pipeline(0, ws, bs, sphere_mode="votes")
 segs, ns = [], [120, 64, 200]
 for i, n in enumerate(ns):
     segs.append(synth.make_scene(4242 + i, n)["segments"])

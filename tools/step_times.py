@@ -17,7 +17,7 @@ ap.add_argument("--verbose", action="store_true")
 a = ap.parse_args()
 name, seg, off = bench.make_workload(a.config, 0, a.images)
 ws, bs = vcnn.random_weights(0)
-pipe = pipeline.Pipeline(0, ws, bs)
+pipe = pipeline.Pipeline(0, ws, bs, sphere_mode="votes")
 pipe.upload(seg, off)
 res, e2e = [], []
 for i in range(a.runs):

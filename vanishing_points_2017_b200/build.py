@@ -38,9 +38,23 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _flags_changed():
+    """Objects built with other flags / VPK_DEFINES must not be linked silently: the flag string of the
+    last build is kept next to the objects."""
+    stamp = os.path.join(OBJ, "flags.txt")
+    cur = " ".join(NVCC_FLAGS)
+    old = open(stamp).read() if os.path.exists(stamp) else None
+    if old != cur:
+        with open(stamp, "w") as fh:
+            fh.write(cur)
+        return True
+    return False
+
+
 def build(force=False, verbose=False):
     nvcc = nvcc_path()
     os.makedirs(OBJ, exist_ok=True)
+    force = _flags_changed() or force
     sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     headers = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(PKG, "..", "include", "vpk.h")]
     jobs = []

@@ -3,12 +3,14 @@ the B200: init_caffe / read_mean_blob / caffe_forward with the same argument
 order.  The forward pass of cnn/deploy.prototxt runs as tcgen05 implicit-GEMM
 kernels behind libvpk.so's C ABI.
 
-The trained caffemodel is an external download (reference README.md:23) and
-Caffe is not needed: `model_weights` may be a dict / .npz of Caffe-layout
-float32 arrays  {conv1_w, conv1_b, ..., fc8_20x20_w, fc8_20x20_b}, or None for
-the seeded random fillers of train/train_val.prototxt.
+The trained caffemodel is an external download (reference README.md:23).  Caffe
+is not needed to use it: `model_weights` may be the `.caffemodel` itself (parsed
+by caffe_proto.py), a dict / .npz of Caffe-layout float32 arrays {conv1_w,
+conv1_b, ..., fc8_20x20_w, fc8_20x20_b}, or None for the seeded random fillers
+of train/train_val.prototxt (benchmarks and tests only: a RuntimeWarning says so).
 """
 import ctypes as C
+import warnings
 
 import numpy as np
 
@@ -74,22 +76,44 @@ def init_caffe(model_def=None, model_weights=None, gpu_id=0):
     evaluation.py:17-22).  model_def is accepted for signature compatibility:
     the architecture is cnn/deploy.prototxt, compiled in."""
     ctx = _lib.default_context(gpu_id)
-    if model_weights is None:
-        ws, bs = random_weights(0)
-    else:
-        src = np.load(model_weights) if isinstance(model_weights, str) else model_weights
-        ws = [src[n + "_w"] for n in LAYER_NAMES]
-        bs = [src[n + "_b"] for n in LAYER_NAMES]
+    ws, bs = load_weights(model_weights)
     return Net(ctx, ws, bs)
+
+
+def load_weights(model_weights, allow_random=False):
+    """The eight (weight, bias) blob pairs of cnn/deploy.prototxt from a .caffemodel, an .npz / dict
+    of `<layer>_w` / `<layer>_b` arrays, or (None) the random fillers of train/train_val.prototxt."""
+    if model_weights is None:
+        if not allow_random:
+            warnings.warn("no CNN weights given: using the seeded random fillers of train/train_val.prototxt -- the "
+                          "response (and every vanishing point initialised from it) is meaningless; pass the "
+                          "reference's weights.caffemodel", RuntimeWarning, stacklevel=3)
+        return random_weights(0)
+    if isinstance(model_weights, str) and not model_weights.endswith(".npz"):
+        from . import caffe_proto
+        layers = caffe_proto.read_caffemodel(model_weights)
+        missing = [n for n in LAYER_NAMES if n not in layers or len(layers[n]) < 2]
+        if missing:
+            raise ValueError("%s: no weight/bias blobs for layers %s (found %s)" % (model_weights, missing, sorted(layers)))
+        ws = [layers[n][0].reshape(shape) for n, shape in zip(LAYER_NAMES, LAYER_SHAPES)]
+        bs = [layers[n][1].reshape(-1) for n in LAYER_NAMES]
+        return ws, bs
+    src = np.load(model_weights) if isinstance(model_weights, str) else model_weights
+    return [src[n + "_w"] for n in LAYER_NAMES], [src[n + "_b"] for n in LAYER_NAMES]
 
 
 def read_mean_blob(mean_file=None):
     """evaluation.read_mean_blob (reference evaluation.py:25-31): returns a
-    (1,1,500,500) float32 array.  Accepts a .npy file; None = zeros (the mean
-    binaryproto is an external download)."""
+    (1,1,500,500) float32 array.  Accepts the reference's mean.binaryproto (BlobProto wire format, parsed
+    by caffe_proto.py) or a .npy file; None = zeros."""
     if mean_file is None:
         return np.zeros((1, 1, 500, 500), dtype=np.float32)
-    return np.asarray(np.load(mean_file), dtype=np.float32).reshape(1, 1, 500, 500)
+    if str(mean_file).endswith(".npy"):
+        arr = np.load(mean_file)
+    else:
+        from . import caffe_proto
+        arr = caffe_proto.read_binaryproto(mean_file)
+    return np.asarray(arr, dtype=np.float32).reshape(1, 1, 500, 500)
 
 
 def caffe_forward(net, image, mean_arr):

@@ -988,6 +988,8 @@ int em_dev(vpk_ctx* ctx, const double* d_lines, const double* d_segments, const 
             VPK_CUDA(cudaMemGetInfo(&free_b, &total_b));
             W.budget = std::max<size_t>((free_b + st->ws.cap) / 2, (size_t)1 << 28) / sizeof(double);
         }
+        // test knob: cap the workspace of a wave (MiB) so that small batches run in several waves
+        if (const char* cap_mb = getenv("VPK_EM_WAVE_MB")) W.budget = std::min<size_t>(W.budget, (size_t)std::max(1, atoi(cap_mb)) * ((size_t)1 << 20) / sizeof(double));
         VPK_TRY(st->h_cnt.ensure(kMaxGroups * 8 * sizeof(int)));
         VPK_TRY(st->ctl.ensure((kMaxGroups + 1) * kCtlInts * sizeof(int)));
         VPK_TRY(st->stats.ensure(32 * sizeof(unsigned long long)));
@@ -1067,6 +1069,9 @@ int vpk_em(vpk_ctx* ctx, const double* lines, const double* segments, const int3
     const int32_t* d_ioff = nullptr;
     if (init_vp) {
         if (!init_vp_offsets) { set_error("vpk_em: init_vp needs init_vp_offsets"); return VPK_ERR_ARG; }
+        if (init_vp_offsets[0] != 0) { set_error("vpk_em: init_vp_offsets[0] must be 0"); return VPK_ERR_ARG; }
+        for (int b = 0; b < B; ++b)
+            if (init_vp_offsets[b + 1] < init_vp_offsets[b]) { set_error("vpk_em: init_vp_offsets must be non-decreasing (B + 1 entries)"); return VPK_ERR_ARG; }
         size_t nv = init_vp_offsets[B];
         VPK_TRY(st->init_vp.ensure((nv + 1) * 3 * sizeof(double)));
         VPK_TRY(st->init_off.ensure((B + 1) * sizeof(int32_t)));

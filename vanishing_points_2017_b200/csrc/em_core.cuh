@@ -129,7 +129,7 @@ VPK_DEV int imin(int a, int b) { return a < b ? a : b; }
 // ---------------------------------------------------------------------------
 struct EmSlot {
     int32_t img, N, base, phase, iter, M, vsel, run_e, run_w, done, status, iters_out;
-    int32_t merge_j, merge_k, after_merge, vidx, npdf, pad0;
+    int32_t merge_j, merge_k, after_merge, vidx, npdf, cap_hit;   // cap_hit: a hypothesis was dropped because kMaxM were live
     double merge_thresh, sigma_prior;
     unsigned long long ws_off;             // doubles from the workspace base
     double cur[kMaxM][3], nxt[kMaxM][3], s[kMaxM];
@@ -668,8 +668,9 @@ VPK_DEVFN void init_prior_and_vps(EmSlot& st, InitScratch& sc, const uint8_t* im
     team_sync();
     if (T.tid == 0) {
         int M = 0;
-        for (int c = 0; c < kCells && M < kMaxM; ++c)
+        for (int c = 0; c < kCells; ++c)
             if (sc.keep[c] && sc.has[c]) {
+                if (M >= kMaxM) { st.cap_hit = 1; break; }       // num_init_vp > 64 maxima: reported as VPK_EM_CAPACITY
                 st.cur[M][0] = sc.cand[c][0]; st.cur[M][1] = sc.cand[c][1]; st.cur[M][2] = sc.cand[c][2];
                 ++M;
             }
@@ -1324,6 +1325,7 @@ VPK_DEVFN int split_best_vp(const Img& im, EmSlot& st, PostScratch& sc, double m
             double c = sc.nv[0][0] * sc.nv[1][0] + sc.nv[0][1] * sc.nv[1][1] + sc.nv[0][2] * sc.nv[1][2];
             c = fmin(fmax(c, -1.0), 1.0);
             double ang = fabs(acos(fmin(fmax(fabs(c), -1.0), 1.0)));
+            if (ang > min_diff && st.M >= kMaxM) st.cap_hit = 1;      // the reference would append; reported as VPK_EM_CAPACITY
             if (ang > min_diff && st.M < kMaxM) {
                 double stdd = st.s[worst] / 2;
                 for (int k = 0; k < 3; ++k) { st.cur[worst][k] = sc.nv[0][k]; st.cur[st.M][k] = sc.nv[1][k]; st.nxt[st.M][k] = 0.0; }
@@ -1343,6 +1345,7 @@ VPK_DEVFN int split_best_vp(const Img& im, EmSlot& st, PostScratch& sc, double m
 // ---------------------------------------------------------------------------
 VPK_DEVFN void write_result(const EmOut& out, const Img& im, EmSlot& st, int status, int iters, bool have_vps, const Team& T) {
     const int N = im.N, b = st.img, base = st.base;
+    if (status == VPK_EM_OK && st.cap_hit) status = VPK_EM_CAPACITY;
     if (T.tid == 0) {
         out.status[b] = status;
         out.iterations[b] = iters;
@@ -1385,10 +1388,12 @@ VPK_DEVFN void request(EmSlot& st, int vsel, int phase, const Team& T, PostScrat
 // ---------------------------------------------------------------------------
 VPK_DEVFN bool init_slot(EmSlot& st, InitScratch& isc, const Img& im, const EmOut& out, const vpk_em_config& cfg,
                          const uint8_t* sphere, int S, const double* init_vp, int n_init, const Team& T) {
-    if (T.tid == 0) { st.M = 0; st.done = 0; st.iter = 0; st.vidx = 0; st.run_e = 0; st.run_w = 0; st.iters_out = 0; }
+    if (T.tid == 0) { st.M = 0; st.done = 0; st.iter = 0; st.vidx = 0; st.run_e = 0; st.run_w = 0; st.iters_out = 0; st.cap_hit = 0; }
     team_sync();
     if (im.N == 0) { write_result(out, im, st, VPK_EM_NO_INITIAL_VPS, 0, false, T); return false; }
     const bool have_init = init_vp != nullptr;
+    // more hypotheses than the slot holds (the reference has no cap): reported, never truncated
+    if (have_init && n_init > kMaxM) { write_result(out, im, st, VPK_EM_CAPACITY, 0, false, T); return false; }
     init_prior_and_vps(st, isc, sphere, S, cfg.num_init_vp, have_init, T);
     if (have_init) {
         if (T.tid == 0) {

@@ -19,11 +19,22 @@ from .vp_localisation import _alloc_result, unpack_results
 class Pipeline:
     """One context (GPU) running the path; CNN weights loaded once."""
 
-    def __init__(self, device=0, weights=None, biases=None, mean=None, sphere_mode="votes", alpha=0.1, size=500,
+    def __init__(self, device=0, weights=None, biases=None, mean=None, sphere_mode=None, alpha=0.1, size=500,
                  **em_kwargs):
+        """weights: list of the eight Caffe-layout weight blobs (with `biases`), or anything
+        cnn.load_weights takes (a .caffemodel / .npz path or dict).  sphere_mode: "curves" is the
+        reference's great-circle line plot (sphere_mapping.py:36-72), what the TRAINED net expects;
+        "votes" is north_star's pairwise-intersection histogram.  Default: "curves" with real
+        weights; without weights the random fillers are used (benchmarks / tests; a RuntimeWarning is
+        raised unless sphere_mode is given explicitly) and the mode defaults to "votes"."""
         self.ctx = _lib.default_context(device)
-        if weights is None:
-            weights, biases = _cnn.random_weights(0)
+        if weights is None or isinstance(weights, (str, dict)) or hasattr(weights, "files"):
+            explicit = sphere_mode is not None
+            if sphere_mode is None:
+                sphere_mode = "votes" if weights is None else "curves"
+            weights, biases = _cnn.load_weights(weights, allow_random=explicit)
+        elif sphere_mode is None:
+            sphere_mode = "curves"
         self.net = _cnn.Net(self.ctx, weights, biases)
         if mean is not None:
             self.net.set_mean(mean)

@@ -86,7 +86,11 @@ def expectation_maximisation_batch(lines, segments, offsets, responses, sphere_i
     iv = ioff = None
     if init_vp is not None:
         iv = _lib.as_f64(init_vp, 3)
+        if init_vp_offsets is None and B != 1:
+            raise ValueError("init_vp for a batch of %d images needs init_vp_offsets (B + 1 entries)" % B)
         ioff = _lib.as_offsets(init_vp_offsets if init_vp_offsets is not None else [0, iv.shape[0]])
+        if ioff.size != B + 1 or ioff[-1] != iv.shape[0]:
+            raise ValueError("init_vp_offsets must have B + 1 = %d entries ending at %d, got %r" % (B + 1, iv.shape[0], ioff))
     arrs, res = _alloc_result(B, int(off[-1]), want_decision_metric)
     _lib.check(ctx.lib.vpk_em(ctx.h, _lib.ptr(lines), _lib.ptr(segments), _lib.ptr(off), B, _lib.ptr(resp),
                               _lib.ptr(sph), S, _lib.ptr(iv), _lib.ptr(ioff), C.byref(cfg), C.byref(res)),
