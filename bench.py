@@ -4,11 +4,16 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--config C] [--impl ours|reference]
 
 One "step" = one pass of the path (segments -> lines -> sphere votes -> CNN ->
-EM -> VPs) over one synthetic batch of BASELINE.json config C (default 2: the
-YUD-shaped batch, 102 images 640x480, ~500 segments, single B200).  With N > 1
-(launched by torch.distributed.run, one rank per GPU) every rank runs its own
-copy of the same batch (fixed per-GPU work): images are independent, so there is no data-path
-collective (weak scaling); the only exchange is the timing reduction.
+EM -> VPs) over one synthetic batch of BASELINE.json config C.
+  N = 1 (default config 2): the YUD-shaped batch, 102 images 640x480, ~500 segments, single B200.
+  N > 1 (default config 4, launched by torch.distributed.run, one rank per GPU): STRONG scaling of
+        the ONE HLW-shaped batch of 2018 images (BASELINE.json configs[3], "sharded across 1/2/4/8
+        B200"; the reference loops per file, evaluation.py:126, 271, 309): rank r runs
+        pipeline.shard_batch(offsets, N, r) (cost-balanced, images are independent, no data-path
+        collective) and the per-image results are gathered on rank 0 INSIDE the timed e2e region;
+        value = 2018 / (max over ranks of the step time).  `--weak` restores the fixed-per-GPU-work mode
+        (every rank runs its own copy of the batch); `--strong` with N = 1 gives the one-GPU figure
+        of the same workload.
 
 value    : whole-job images/s with the batch already resident in HBM (device
            time from CUDA events on the launching stream, max over ranks).
@@ -178,12 +183,52 @@ def time_oracle(seg, off, weights, biases, sample, repeats=1):
     return sample / dt, dt
 
 
+def time_reference_em(seg, off, weights, biases, sample):
+    """The reference's OWN EM (vp_localisation.expectation_maximisation, Python-3-patched copy in the
+    git-ignored baseline/_ref/, written by __graft_entry__.build() where /root/reference exists; BASELINE.md
+    section 3) on `sample` images of the batch, joblib on all host cores like the original.  Sphere image and
+    CNN response come from the port (matplotlib / Caffe are not installable).  None if baseline/_ref is absent."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "vp_localisation.py")):
+        return None
+    import contextlib
+    import io
+    import warnings
+    from oracle import cnn_oracle, ref_patch, sphere_oracle
+    try:
+        vp, _ = ref_patch.load(ref_dir)
+    except Exception as e:                       # e.g. sklearn / joblib missing on the box
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+    idx = np.linspace(0, len(off) - 2, sample).astype(int)
+    prep = []
+    for i in idx:
+        sgm = seg[off[i]:off[i + 1]]
+        lines = synth.lines_from_segments(sgm)
+        img = sphere_oracle.votes_to_image(sphere_oracle.sphere_votes(lines, 500))
+        sig, _ = cnn_oracle.forward(img[None], weights, biases)
+        prep.append((lines, sgm.copy(), sig[0].astype(np.float64), img))
+    t0 = time.perf_counter()
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        for lines, sgm, sig, img in prep:
+            try:
+                vp.expectation_maximisation(lines, sgm, sig, sphere_image=img, distance_measure="angle", use_weights=True,
+                                            do_split=True, do_merge=True)
+            except ValueError:
+                pass
+    dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": "images/s (EM stage only)", "seconds": dt, "images": int(sample),
+            "segments": [int(off[i + 1] - off[i]) for i in idx], "cores": os.cpu_count() or 1,
+            "what": "UNMODIFIED arithmetic of the reference's vp_localisation.expectation_maximisation "
+                    "(five mechanical Python-3 patches, baseline/_ref/), joblib over all cores"}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU path on the box's host cores, rank 0 only."""
     if rank != 0:
         return
     from oracle import cnn_oracle
-    name, seg, off = make_workload(args.config, 0)
+    name, seg, off = make_workload(args.config, 0, args.images)
     ws, bs = cnn_oracle.random_weights(0, scale=args.weight_scale)
     sample = 2
     for _ in range(args.warmup):
@@ -194,6 +239,7 @@ def run_reference(args, rank, world):
     dt = (time.perf_counter() - t0) / args.steps
     v = sample / dt
     cores = os.cpu_count() or 1
+    ref_em = None if args.no_reference_em else time_reference_em(seg, off, ws, bs, 2)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -201,7 +247,8 @@ def run_reference(args, rank, world):
                        "sample": "%d images per step, evenly spaced over the %d-image batch" % (sample, len(off) - 1)},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d images/step of the same batch; numpy+torch CPU oracle (oracle/), "
-                                       "BLAS/torch threads = %d" % (sample, cores)},
+                                       "BLAS/torch threads = %d" % (sample, cores),
+                             "reference_em": ref_em},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -216,8 +263,16 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     peaks = load_peaks()
-    # weak scaling with FIXED per-GPU work: every rank processes the same synthetic batch
-    name, seg, off = make_workload(args.config, 0, args.images)
+    name, seg_all, off_all = make_workload(args.config, 0, args.images)
+    B_all = len(off_all) - 1
+    if args.strong:
+        # STRONG scaling: the one batch is sharded (LPT on the N^2 + const cost model); rank r owns images `idx`
+        idx = pipeline.shard_batch(off_all, world, rank)
+        seg, off = pipeline.take_images(seg_all, off_all, idx)
+    else:
+        # weak scaling with FIXED per-GPU work: every rank processes the same synthetic batch
+        idx = np.arange(B_all)
+        seg, off = seg_all, off_all
     B = len(off) - 1
     ws, bs = vcnn.random_weights(0, scale=args.weight_scale)
     pipe = pipeline.Pipeline(local_rank, ws, bs, sphere_mode=args.sphere_mode)
@@ -292,20 +347,54 @@ def run_ours(args, rank, world, local_rank):
         pipe(seg_pin.numpy(), off_pin.numpy(), raw=True)
     barrier()
     t0 = time.perf_counter()
+    gather_ms = 0.0
     for _ in range(args.steps):
         flush_l2()
         out = pipe(seg_pin.numpy(), off_pin.numpy(), raw=True)
+        if args.strong and world > 1:
+            # the path's only exchange: the per-image results of every shard end up on rank 0
+            tg = time.perf_counter()
+            full = pipeline.gather_raw(out, idx, off, B_all, world, dist)
+            gather_ms += (time.perf_counter() - tg) * 1e3
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     h2d = seg.nbytes + off.nbytes
     d2h = sum(a.nbytes for a in out.values() if a is not None)
+    n_ok_all = None
+    if args.strong and world > 1 and rank == 0:
+        n_ok_all = int(np.sum(full["status"] == 0))
+        assert full["status"].shape[0] == B_all and int(full["offsets"][-1]) == int(off_all[-1])
+
+    # ---- strong scaling: the one-GPU figure of the SAME batch, measured by rank 0 in this very run
+    one_gpu = None
+    if args.strong and world > 1:
+        if rank == 0:
+            sa, oa = torch.from_numpy(seg_all).pin_memory(), torch.from_numpy(off_all).pin_memory()
+            for _ in range(2):
+                pipe(sa.numpy(), oa.numpy(), raw=True)
+            ctx.synchronize()
+            k1 = max(1, min(args.steps, 3))
+            t1 = time.perf_counter()
+            for _ in range(k1):
+                flush_l2()
+                pipe(sa.numpy(), oa.numpy(), raw=True)
+            ctx.synchronize()
+            one_gpu = {"e2e_images_per_s": B_all * k1 / (time.perf_counter() - t1), "steps": k1}
+        barrier()
 
     # ---- reduce over ranks: max time, total images
     t = torch.tensor([dev_ms / args.steps, e2e_ms, wall_ms / args.steps], dtype=torch.float64, device="cuda")
+    tmin = t.clone()
+    nimg = torch.tensor([float(B), float(n_ok)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(nimg, op=dist.ReduceOp.SUM)
     ms_step, e2e_step, wall_step = [float(x) for x in t.tolist()]
-    total_images = B * world
+    total_images = int(nimg[0].item())
+    n_ok = int(nimg[1].item())
+    if args.strong:
+        assert total_images == B_all
 
     if rank == 0:
         # dominant kernel (largest share of the profiled steps) and its roofline
@@ -382,21 +471,32 @@ def run_ours(args, rank, world, local_rank):
             cores = os.cpu_count() or 1
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "%d of the %d images (evenly spaced), %.1f s; numpy+torch CPU oracle (oracle/), "
-                             "BLAS/torch threads = %d" % (sample, B, dt, cores)}
+                             "BLAS/torch threads = %d" % (sample, B, dt, cores),
+                   "reference_em": None if args.no_reference_em else time_reference_em(seg, off, ws, bs, 2)}
 
         line = {
             "metric": METRIC, "value": total_images / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (sphere, EM) + bf16/f32-accumulate (CNN)",
+            "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+            "dtype": "f64 (sphere, EM) + bf16/f32-accumulate (CNN)",
             "data": "synthetic",
             "config": {"workload": "%s-shaped synthetic batch (BASELINE.json configs[%d])" % (name, args.config - 1),
-                       "images_per_gpu": B, "segments_per_image_mean": float(np.mean(np.diff(off))),
+                       "images": total_images, "images_on_rank0": B,
+                       "segments_per_image_mean": float(np.mean(np.diff(off_all))),
                        "sphere_size": 500, "sphere_mode": args.sphere_mode, "cnn_weights": "random-init "
                        "(train_val.prototxt fillers x%g, seed 0)" % args.weight_scale,
                        "l2": "flushed between steps (256 MiB memset)",
-                       "parallelism": "images sharded, no collective; every rank runs the same batch (fixed per-GPU work)"},
+                       "parallelism": ("ONE batch sharded over the ranks (pipeline.shard_batch: LPT on N^2 + const), no data-path "
+                                       "collective, results gathered on rank 0 inside the e2e region" if args.strong else
+                                       "images sharded, no collective; every rank runs the same batch (fixed per-GPU work)")},
             "e2e": {"value": total_images / (e2e_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_step},
+            "strong_scaling": None if not (args.strong and world > 1) else {
+                "one_gpu_same_batch": one_gpu,
+                "speedup_e2e": (total_images / (e2e_step * 1e-3)) / one_gpu["e2e_images_per_s"] if one_gpu else None,
+                "rank_time_ms": {"resident_max": ms_step, "resident_min": float(tmin[0].item()),
+                                 "e2e_max": e2e_step, "e2e_min": float(tmin[1].item())},
+                "gather_ms_per_step_rank0": gather_ms / args.steps, "images_with_vps_after_gather": n_ok_all},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
@@ -425,7 +525,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
+    ap.add_argument("--config", type=int, default=None, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config (1-based); default 2 (YUD) on one GPU, 4 (HLW, sharded) on several")
+    ap.add_argument("--strong", action="store_true", help="shard ONE batch over the ranks (default for --gpus > 1)")
+    ap.add_argument("--weak", action="store_true", help="every rank runs its own copy of the batch")
+    ap.add_argument("--no-reference-em", action="store_true", help="skip the reference's own EM in the CPU baseline")
     ap.add_argument("--images", type=int, default=None, help="override the number of images per GPU")
     ap.add_argument("--sphere-mode", default="votes", choices=["votes", "curves"])
     ap.add_argument("--weight-scale", type=float, default=1.0,
@@ -439,6 +543,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not args.weak and world > 1:
+        args.strong = True
+    if args.weak:
+        args.strong = False
+    if args.config is None:
+        args.config = 4 if args.strong else 2
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

@@ -29,27 +29,8 @@ sys.path.insert(0, ROOT)
 
 
 def load_reference():
-    tmp = tempfile.mkdtemp(prefix="vpref_")
-    for name in ("vp_localisation", "probability_functions", "coordinate_conversion", "calc_horizon"):
-        src = open(os.path.join(REF, name + ".py")).read()
-        src = re.sub(r'^(\s*)print (.+)$', r'\1print(\2)', src, flags=re.M)
-        src = src.replace("np.linalg.linalg.LinAlgError", "np.linalg.LinAlgError")
-        src = src.replace("affinity='precomputed'", "metric='precomputed'")
-        src = src.replace("np.array(to_be_removed)", "np.array(to_be_removed, dtype=int)")
-        if name == "vp_localisation":
-            src = src.replace("ra*sA/rA:(ra+1)*sA/rA, rb*sB/rB:(rb+1)*sB/rB",
-                              "ra*sA//rA:(ra+1)*sA//rA, rb*sB//rB:(rb+1)*sB//rB")
-            src = src.replace("max_response[0] + ra*sA/rA", "max_response[0] + ra*sA//rA")
-            src = src.replace("max_response[1] + rb*sB/rB", "max_response[1] + rb*sB//rB")
-        with open(os.path.join(tmp, name + ".py"), "w") as fh:
-            fh.write(src)
-    sys.path.insert(0, tmp)
-    os.environ["PYTHONPATH"] = tmp + os.pathsep + os.environ.get("PYTHONPATH", "")
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        vp = importlib.import_module("vp_localisation")
-        prob = importlib.import_module("probability_functions")
-    return vp, prob
+    from oracle import ref_patch
+    return ref_patch.load(ref_patch.materialise(tempfile.mkdtemp(prefix="vpref_")))
 
 
 def main():

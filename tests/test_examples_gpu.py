@@ -46,7 +46,7 @@ def test_example_images_stage_by_stage():
     rsig, rlog = cnn_oracle.forward(sph, ws, bs)
     assert np.max(np.abs(sig - rsig)) <= 0.25 * 1e-2 * np.max(np.abs(rlog)) + 1e-6
     # E0-E12 on the pipeline's own response and sphere image; N1 on the EM result
-    decided = 0
+    decided, boundary = 0, []
     rs = np.random.RandomState(0)
     hz = pipe.horizons(maxbest=20)
     for i in range(n):
@@ -68,9 +68,18 @@ def test_example_images_stage_by_stage():
             # an image on a decision boundary of the reference algorithm itself decides nothing
             flips = sum(0 if same_vps(oracle_em(s * (1.0 + 1e-14 * rs.standard_normal(s.shape))), ref) else 1 for _ in range(3))
             assert flips > 0, "image %d: VPs differ from an oracle that is stable under perturbation" % i
+            boundary.append(i)
         if res[i]["vp"] is not None:
             h = horizon_oracle.calculate_horizon_and_ortho_vp(res[i], maxbest=20)
             np.testing.assert_array_equal(hz[i][5], np.asarray(h[5]).reshape(-1))
             for q in range(5):
                 np.testing.assert_allclose(hz[i][q], h[q], rtol=1e-9, atol=1e-12, equal_nan=True)
-    assert decided >= 3
+    # the set of decision-boundary images is pinned: a regression that turns a stable image into a skipped one fails here
+    assert boundary == EXPECTED_BOUNDARY_IMAGES, "images skipped as decision-boundary cases: %r (pinned: %r)" % (
+        boundary, EXPECTED_BOUNDARY_IMAGES)
+    assert decided == n - len(EXPECTED_BOUNDARY_IMAGES)
+
+
+# Images of assets/examples whose EM result flips in the ORACLE itself under a 1e-14 relative perturbation of the
+# segments with this CNN response; measured on the B200 box, `profiles/r2_parity_report.txt`.
+EXPECTED_BOUNDARY_IMAGES = []

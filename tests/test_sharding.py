@@ -62,3 +62,61 @@ def test_gather_results_gloo_world2():
         assert p.exitcode == 0
     assert [g[0] for g in got] == list(range(11))
     assert {g[1] for g in got} == {0, 1}
+
+
+def _fake_raw(idx, n):
+    """Flat result arrays as vp_localisation._alloc_result lays them out, filled with values that encode
+    the global image index."""
+    B, M = len(idx), 64
+    off = np.concatenate([[0], np.cumsum(n)]).astype(np.int32)
+    arrs = {"status": np.zeros(B, np.int32), "n_vp": (np.asarray(idx) % 5 + 1).astype(np.int32),
+            "iterations": np.asarray(idx, np.int32) * 2, "vp": np.zeros((B, M, 3)), "sigma": np.zeros((B, M)),
+            "counts": np.zeros((B, M), np.int32), "counts_weighted": np.zeros((B, M)),
+            "vp_assoc": np.full(max(int(off[-1]), 1) + 7, -5, np.int32)}       # longer than sum N, like a reused buffer
+    for k, i in enumerate(idx):
+        arrs["vp"][k, 0] = [i, i + 0.5, -i]
+        arrs["vp_assoc"][off[k]:off[k + 1]] = i
+    return arrs, off
+
+
+def _worker_raw(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_all = np.array([30, 0, 75, 12, 51, 9, 64])
+    off_all = np.concatenate([[0], np.cumsum(n_all)])
+    idx = pipeline.shard_batch(off_all, world, rank)
+    arrs, off = _fake_raw(idx, n_all[idx])
+    out = pipeline.gather_raw(arrs, idx, off, len(n_all), world, dist)
+    if rank == 0:
+        q.put({k: v for k, v in out.items()})
+    else:
+        assert out is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_raw_gloo_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_raw, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n_all = np.array([30, 0, 75, 12, 51, 9, 64])
+    np.testing.assert_array_equal(out["offsets"], np.concatenate([[0], np.cumsum(n_all)]))
+    np.testing.assert_array_equal(out["iterations"], np.arange(7) * 2)
+    np.testing.assert_array_equal(out["vp"][:, 0, 0], np.arange(7.0))
+    np.testing.assert_array_equal(out["vp_assoc"], np.repeat(np.arange(7), n_all))
+    # single rank: identity up to the image order
+    arrs, off = _fake_raw(np.array([2, 0, 1]), np.array([5, 3, 4]))
+    one = pipeline.gather_raw(arrs, np.array([2, 0, 1]), off, 3, 1)
+    np.testing.assert_array_equal(one["vp_assoc"], np.repeat([0, 1, 2], [3, 4, 5]))

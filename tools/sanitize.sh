@@ -1,0 +1,26 @@
+#!/bin/bash
+# compute-sanitizer over the kernels with hand-rolled synchronisation: the mbarrier /
+# bulk-copy ring of the weight-matrix pass, the cluster / distributed-shared-memory code and the ticket
+# counters that close a superstep, the tcgen05 / TMA GEMM, the sphere-vote atomics.
+# usage: tools/sanitize.sh TAG     (GPU box; summaries under gpurun_out/TAG_sanitize_*.txt)
+TAG=${1:-rX}
+mkdir -p gpurun_out
+CS=/usr/local/cuda/bin/compute-sanitizer
+run() {   # name, tool, extra env, command...
+    local name=$1 tool=$2; shift 2
+    timeout 900 $CS --tool $tool --print-limit 20 --error-exitcode 9 "$@" > gpurun_out/${TAG}_sanitize_${name}_${tool}.log 2>&1
+    local rc=$?
+    { echo "== $name / $tool: exit $rc"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard|Invalid|images with VPs|passed|failed" gpurun_out/${TAG}_sanitize_${name}_${tool}.log | sort | uniq -c | head -20; } \
+        >> gpurun_out/${TAG}_sanitize_summary.txt
+}
+rm -f gpurun_out/${TAG}_sanitize_summary.txt
+# the whole path on a small YUD-shaped batch (device-driven EM loop)
+run pipe12 memcheck python tools/run_once.py --config 2 --images 12
+run pipe12 racecheck python tools/run_once.py --config 2 --images 12
+# host-driven loop (ordinary launches)
+VPK_EM_HOST_LOOP=1 run pipe12_hostloop racecheck python tools/run_once.py --config 2 --images 12
+# one large image: N = 1600 takes the paths above the slab-split threshold (1536)
+run em1600 memcheck python tools/run_em_once.py --n 1600
+run em1600 racecheck python tools/run_em_once.py --n 1600
+run em3200 racecheck python tools/run_em_once.py --n 3200 --num-iter 3
+cat gpurun_out/${TAG}_sanitize_summary.txt

@@ -23,6 +23,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 struct CnnState {
     bool loaded = false;
+    bool attr3 = false, attr4 = false;     // dynamic shared-memory opt-in of the two GEMM instantiations: per CONTEXT (device)
     EncodeTiledFn encode = nullptr;
     // bf16 weight matrices (K-major) and fp32 biases, one per layer conv1..fc8
     DBuf w[8], b[8], mean;
@@ -251,12 +252,12 @@ int launch_gemm(vpk_ctx* ctx, const GemmCall& c) {
     KernelScope ks(ctx, c.name);
     if (c.p.bn <= 128) {
         size_t smem = 3 * stage + 1024;
-        static bool attr3 = false;
+        bool& attr3 = st->attr3;
         if (!attr3) { VPK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (kABytes + 128 * kBK * 2) + 1024)); attr3 = true; }
         gemm_bf16_tcgen05_kernel<3><<<grid, kGemmThreads, smem, ctx->stream>>>(ma, mb, c.p);
     } else {
         size_t smem = 4 * stage + 1024;
-        static bool attr4 = false;
+        bool& attr4 = st->attr4;
         if (!attr4) { VPK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (kABytes + 256 * kBK * 2) + 1024)); attr4 = true; }
         gemm_bf16_tcgen05_kernel<4><<<grid, kGemmThreads, smem, ctx->stream>>>(ma, mb, c.p);
     }

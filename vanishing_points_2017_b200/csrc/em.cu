@@ -771,7 +771,7 @@ static int plan_wave(vpk_ctx* ctx, EmState* st, const EmParams& P0, const int32_
     // groups: the wave's images (heaviest first) are dealt round-robin, so every group gets the same
     // mix of sizes; a group's slots are contiguous.  One group per ~kGroupSlots images.
     static const int env_groups = getenv("VPK_EM_GROUPS") ? atoi(getenv("VPK_EM_GROUPS")) : 0;
-    static const bool host_loop_env = getenv("VPK_EM_HOST_LOOP") != nullptr;
+    const bool host_loop_env = getenv("VPK_EM_HOST_LOOP") != nullptr;     // read per call: smoke() toggles it
     W.device_loop = !host_loop_env && !ctx->profiling;   // no per-kernel events inside a graph
     int G = env_groups > 0 ? env_groups : (n + kGroupSlots - 1) / kGroupSlots;
     G = std::max(1, std::min(G, std::min(n, kMaxGroups)));

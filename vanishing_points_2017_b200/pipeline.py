@@ -170,3 +170,38 @@ def gather_results(local_results, idx, n_images, world_size, dist=None):
         for i, r in part:
             out[i] = r
     return out
+
+
+RAW_PER_IMAGE = ("status", "n_vp", "iterations", "vp", "sigma", "counts", "counts_weighted")
+
+
+def gather_raw(arrs, idx, offsets, n_images, world_size, dist=None):
+    """gather_results for the flat result arrays (`raw=True`): every rank contributes the arrays of its
+    shard (images `idx`, local `offsets`); rank 0 returns them reassembled in the batch's image order
+    (plus "offsets", the batch's (n_images + 1) prefix sums, for vp_assoc), the other ranks None."""
+    payload = {k: arrs[k] for k in RAW_PER_IMAGE}
+    payload["vp_assoc"] = arrs["vp_assoc"][:int(offsets[-1])]
+    payload["idx"] = np.asarray(idx, dtype=np.int64)
+    payload["n"] = np.diff(np.asarray(offsets, dtype=np.int64))
+    if dist is None or world_size == 1:
+        parts = [payload]
+    else:
+        parts = [None] * world_size if dist.get_rank() == 0 else None
+        dist.gather_object(payload, parts, dst=0)
+        if dist.get_rank() != 0:
+            return None
+    n = np.zeros(n_images, dtype=np.int64)
+    for p in parts:
+        n[p["idx"]] = p["n"]
+    off = np.zeros(n_images + 1, dtype=np.int64)
+    off[1:] = np.cumsum(n)
+    out = {k: np.empty((n_images,) + parts[0][k].shape[1:], dtype=parts[0][k].dtype) for k in RAW_PER_IMAGE}
+    out["vp_assoc"] = np.empty(int(off[-1]), dtype=np.int32)
+    out["offsets"] = off
+    for p in parts:
+        for k in RAW_PER_IMAGE:
+            out[k][p["idx"]] = p[k]
+        lo = np.concatenate([[0], np.cumsum(p["n"])])
+        for j, i in enumerate(p["idx"]):
+            out["vp_assoc"][off[i]:off[i + 1]] = p["vp_assoc"][lo[j]:lo[j + 1]]
+    return out
