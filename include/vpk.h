@@ -157,6 +157,10 @@ VPK_API int vpk_em(vpk_ctx* ctx, const double* lines, const double* segments, co
  * (the planes w, lvsq, pvl of every active image once per superstep: 8 (3 M N + 5 N)),
  * out[5] = of the E-step kernel (same figure: three planes written). */
 VPK_API int vpk_em_stats(vpk_ctx* ctx, uint64_t out[6], int reset);
+/* Profiling runs only: SM cycles the leading CTA of every image's cluster spent per phase of the fused
+ * EM kernel since the last reset: out[0] E-step, [1] barrier after E, [2] weight-matrix product, [3] barrier
+ * after W, [4] M-step sums spread over the cluster, [5] POST (state machine), [6] barrier + state mirror. */
+VPK_API int vpk_em_phase_cycles(vpk_ctx* ctx, uint64_t out[8], int reset);
 
 /* ---- whole path ---------------------------------------------------------- */
 /* example.py:37-39 / benchmark.py:59-66 for a ragged batch, without the

@@ -133,3 +133,25 @@ def test_kwargs_and_errors(em):
     ref = vo.expectation_maximisation(sc["lines"].copy(), sc["segments"].copy(), resp.copy(), sphere_image=img, init_vp=iv)
     res = em.expectation_maximisation(sc["lines"].copy(), sc["segments"].copy(), resp.copy(), sphere_image=img, init_vp=iv)
     compare(res, ref["vp"], ref["counts"], ref["vp_assoc"], ref["sigma"], ref["iterations"])
+
+
+@pytest.mark.parametrize("N", [450, 1700])
+def test_loop_modes_are_bit_identical(em, monkeypatch, N):
+    """The superstep loop runs as one persistent kernel with a cluster per image (default), as a CUDA graph of
+    conditional WHILE nodes, or driven by the host; the weight-matrix product keeps the same chunk ranges and
+    summation order in all three, so the results must agree bit for bit (N = 1700: two chunk ranges per slab)."""
+    sc = synth.make_scene(9100 + N, N, 800, 600, noise_deg=1.0)
+    img = so.votes_to_image(so.sphere_votes(sc["lines"], 500))
+    resp = synth.ideal_response(sc["vps"], seed=N)
+    out = {}
+    for mode, cl in (("fused", "8"), ("fused", "2"), ("fused", "1"), ("graph", "8"), ("host", "8")):
+        monkeypatch.setenv("VPK_EM_MODE", mode)
+        monkeypatch.setenv("VPK_EM_CLUSTER", cl)
+        out[(mode, cl)] = em.expectation_maximisation(sc["lines"].copy(), sc["segments"].copy(), resp.copy(), sphere_image=img)
+    ref = out[("host", "8")]
+    assert ref["vp"] is not None and ref["iterations"] >= 3
+    for key, res in out.items():
+        assert res["iterations"] == ref["iterations"], key
+        np.testing.assert_array_equal(res["vp"], ref["vp"], err_msg=str(key))
+        np.testing.assert_array_equal(res["vp_assoc"], ref["vp_assoc"], err_msg=str(key))
+        np.testing.assert_array_equal(res["decision_metric"], ref["decision_metric"], err_msg=str(key))

@@ -55,7 +55,6 @@ def test_large_images_against_oracle(em, seed, N, noise, kw):
     sc, img, resp = scene(7100 + seed, N, noise)
     ref = vo.expectation_maximisation(sc["lines"].copy(), sc["segments"].copy(), resp.copy(), sphere_image=img, **kw)
     res = em.expectation_maximisation(sc["lines"].copy(), sc["segments"].copy(), resp.copy(), sphere_image=img, **kw)
-    assert ref["iterations"] >= 8
     compare(res, ref)
 
 

@@ -19,7 +19,7 @@ EM_OK, EM_NO_INITIAL_VPS, EM_NO_VPS_LEFT, EM_CAPACITY = 0, 1, 2, 3
 SYMBOLS = [
     "vpk_create", "vpk_destroy", "vpk_abi_version", "vpk_last_error", "vpk_synchronize", "vpk_launch_count",
     "vpk_profile_enable", "vpk_profile_reset", "vpk_profile_read", "vpk_lines_from_segments", "vpk_sphere_map",
-    "vpk_cnn_load", "vpk_cnn_forward", "vpk_debug_gemm", "vpk_em_default_config", "vpk_em", "vpk_em_stats", "vpk_pipeline_upload", "vpk_pipeline_run",
+    "vpk_cnn_load", "vpk_cnn_forward", "vpk_debug_gemm", "vpk_em_default_config", "vpk_em", "vpk_em_stats", "vpk_em_phase_cycles", "vpk_pipeline_upload", "vpk_pipeline_run",
     "vpk_pipeline_fetch", "vpk_pipeline_host", "vpk_pipeline_stage_ms", "vpk_horizon", "vpk_pipeline_horizon",
     "vpk_segments_from_lsd", "vpk_pipeline_upload_lsd",
 ]
@@ -80,6 +80,7 @@ def load():
         lib.vpk_em.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(EmConfig), C.POINTER(EmResult)]
         lib.vpk_em_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        lib.vpk_em_phase_cycles.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         lib.vpk_pipeline_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         lib.vpk_pipeline_run.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.POINTER(EmConfig)]
         lib.vpk_pipeline_fetch.argtypes = [C.c_void_p, C.POINTER(EmResult), C.c_void_p, C.c_void_p]
@@ -149,6 +150,12 @@ class Context:
         check(self.lib.vpk_em_stats(self.h, out, 1 if reset else 0), "vpk_em_stats")
         return {"wmat_bytes": int(out[0]), "wmat_flops": int(out[1]), "wmat_products": int(out[2]),
                 "supersteps": int(out[3]), "post_bytes": int(out[4]), "estep_bytes": int(out[5])}
+
+    def em_phase_cycles(self, reset=False):
+        out = (C.c_uint64 * 8)()
+        check(self.lib.vpk_em_phase_cycles(self.h, out, 1 if reset else 0), "vpk_em_phase_cycles")
+        names = ["estep", "sync_e", "wmat", "sync_w", "mstep_sums", "post", "sync_mirror"]
+        return {n: int(out[i]) for i, n in enumerate(names)}
 
     def profile_read(self):
         cap = 64

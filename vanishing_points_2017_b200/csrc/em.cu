@@ -32,6 +32,7 @@
 #include <vector>
 #include <chrono>
 #include <cstdio>
+#include <cstring>
 #include "em_core.cuh"
 #include "vpk_internal.cuh"
 
@@ -273,27 +274,23 @@ __global__ void __launch_bounds__(kInitThreads) em_init_kernel(EmParams P) {
 // warp order; the W operand tile is staged in shared memory and written with
 // contiguous stores.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kEThreads) em_estep_kernel(EmParams P) {
-    constexpr int NW = kEThreads / 32, kMI = kMaxM / NW;
-    __shared__ double c_pv[kMaxM], c_vx[kMaxM], c_vy[kMaxM], c_inv2s[kMaxM], c_coef[kMaxM];
-    __shared__ double s_pl[NW][32];
-    __shared__ double s_wt[kMaxM / kMP][32][kMP + 1];       // +1: conflict-free column writes
-    const int cur = P.ctl[3] & 1;
-    if ((int)blockIdx.y >= P.ctl[cur]) return;
-    const int slot = P.lists[cur * P.n_slots + blockIdx.y];
-    const EmSlot& st = P.slots[slot];
-    if (!st.run_e) return;
-    const int N = st.N, M = st.M, n0 = blockIdx.x * 32;
-    if (n0 >= N) return;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // algorithmic bytes of this slot's E-step: segments + line weights in, the planes lvsq, pvl, wt out
-    if (P.stats && blockIdx.x == 0 && tid == 0) atomicAdd(P.stats + 4, 8ull * (5ull * N + 3ull * M * N));
-    for (int m = tid; m < M; m += kEThreads) {
-        c_pv[m] = st.pv[m]; c_vx[m] = st.vx[m]; c_vy[m] = st.vy[m]; c_inv2s[m] = st.inv2s[m]; c_coef[m] = st.coef[m];
+struct ESmem {
+    double c_pv[kMaxM], c_vx[kMaxM], c_vy[kMaxM], c_inv2s[kMaxM], c_coef[kMaxM];
+    double s_pl[kEThreads / 32][32];
+    double s_wt[kMaxM / kMP][32][kMP + 1];       // +1: conflict-free column writes
+};
+
+// the constants of the E-step on the slot's selected VP set (prepare_estep) -> shared memory
+__device__ __forceinline__ void estep_load_constants(ESmem& es, const EmSlot& st) {
+    for (int m = threadIdx.x; m < st.M; m += blockDim.x) {
+        es.c_pv[m] = st.pv[m]; es.c_vx[m] = st.vx[m]; es.c_vy[m] = st.vy[m]; es.c_inv2s[m] = st.inv2s[m]; es.c_coef[m] = st.coef[m];
     }
-    __syncthreads();
-    const Img im = make_img(N, P.ws + st.ws_off, P.segs + 4 * (size_t)st.base);
-    const uint64_t keep = em_policy_keep();
+}
+
+// E5 for lines n0 .. n0+31 of one image (block-wide, kEThreads threads; es.c_* loaded and synchronised)
+__device__ __forceinline__ void estep_tile(ESmem& es, const Img& im, int N, int M, int n0, uint64_t keep) {
+    constexpr int NW = kEThreads / 32, kMI = kMaxM / NW;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = n0 + lane;
     const bool live = n < N;
     const LineGeom g = line_geom(im.lp, live ? n : 0);
@@ -305,16 +302,16 @@ __global__ void __launch_bounds__(kEThreads) em_estep_kernel(EmParams P) {
         plv[mi] = 0.0;
         if (m < M) {
             double lvsq;
-            estep_nm(g, c_vx[m], c_vy[m], c_inv2s[m], c_coef[m], lvsq, plv[mi]);
+            estep_nm(g, es.c_vx[m], es.c_vy[m], es.c_inv2s[m], es.c_coef[m], lvsq, plv[mi]);
             if (live) em_st_keep(im.lvsq + (size_t)m * N + n, lvsq, keep);
-            part += plv[mi] * c_pv[m];
+            part += plv[mi] * es.c_pv[m];
         }
     }
-    s_pl[warp][lane] = part;
+    es.s_pl[warp][lane] = part;
     __syncthreads();
     double pl = 0.0;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) pl += s_pl[w][lane];
+    for (int w = 0; w < NW; ++w) pl += es.s_pl[w][lane];
     if (pl < 1e-12) pl = 1e-12;                                         // :117 (NaN stays NaN)
     const double inv_pl = 1.0 / pl;
     const double lw = live ? im.lweight[n] : 0.0;
@@ -325,11 +322,11 @@ __global__ void __launch_bounds__(kEThreads) em_estep_kernel(EmParams P) {
         if (p < passes && mm < wpass_stride(M, p)) {
             double x = 0.0;
             if (m < M) {
-                x = plv[mi] * c_pv[m] * inv_pl;                         // calc_pvl (:128)
+                x = plv[mi] * es.c_pv[m] * inv_pl;                      // calc_pvl (:128)
                 if (live) em_st_keep(im.pvl + (size_t)m * N + n, x, keep);
                 x *= lw;                                                // weight_matrix :517
             }
-            s_wt[p][lane][mm] = x;
+            es.s_wt[p][lane][mm] = x;
         }
     }
     __syncthreads();
@@ -337,8 +334,25 @@ __global__ void __launch_bounds__(kEThreads) em_estep_kernel(EmParams P) {
     for (int p = 0; p < passes; ++p) {
         const int ws = wpass_stride(M, p);
         double* dst = im.wt + (size_t)p * N * kMP + (size_t)n0 * ws;
-        for (int e = tid; e < nl * ws; e += kEThreads) em_st_keep(dst + e, s_wt[p][e / ws][e % ws], keep);
+        for (int e = tid; e < nl * ws; e += kEThreads) em_st_keep(dst + e, es.s_wt[p][e / ws][e % ws], keep);
     }
+}
+
+__global__ void __launch_bounds__(kEThreads) em_estep_kernel(EmParams P) {
+    __shared__ ESmem es;
+    const int cur = P.ctl[3] & 1;
+    if ((int)blockIdx.y >= P.ctl[cur]) return;
+    const int slot = P.lists[cur * P.n_slots + blockIdx.y];
+    const EmSlot& st = P.slots[slot];
+    if (!st.run_e) return;
+    const int N = st.N, M = st.M, n0 = blockIdx.x * 32;
+    if (n0 >= N) return;
+    // algorithmic bytes of this slot's E-step: segments + line weights in, the planes lvsq, pvl, wt out
+    if (P.stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.stats + 4, 8ull * (5ull * N + 3ull * M * N));
+    estep_load_constants(es, st);
+    __syncthreads();
+    const Img im = make_img(N, P.ws + st.ws_off, P.segs + 4 * (size_t)st.base);
+    estep_tile(es, im, N, M, n0, em_policy_keep());
 }
 
 // ---------------------------------------------------------------------------
@@ -596,6 +610,219 @@ __global__ void __launch_bounds__(kPostThreads) em_post_kernel(EmParams P, TierC
 }
 
 // ---------------------------------------------------------------------------
+// em_fused: the whole superstep loop of an image inside ONE persistent kernel.
+//
+// A thread-block cluster owns an image from its first E-step to its result: the
+// slot state lives in the shared memory of the cluster's CTA 0 (the other CTAs
+// mirror the few words they need through distributed shared memory), and the
+// three phases of a superstep are separated by cluster barriers instead of
+// kernel boundaries:
+//     E     : CTA r takes the 32-line tiles r, r + C, ...
+//     W     : CTA r takes the 64-column slabs r, r + C, ... (the same bulk-copy ring,
+//             the same chunk ranges and summation order as em_wmat: bit-identical w)
+//     POST  : CTA 0 runs the state machine (post_slot); the sums of the M-step,
+//             one warp per hypothesis, are spread over the warps of ALL CTAs first
+//     (E + W + POST of one image never wait for another image)
+// Clusters pull images from a queue (heaviest first) until it is empty, two CTAs
+// per SM, so the POST of one image overlaps the W of the image that shares its SMs,
+// and the similarity matrices of the ~40-70 images in flight stay in the L2.
+// ---------------------------------------------------------------------------
+constexpr int kFThreads = 256;
+static_assert(kFThreads == kEThreads && kFThreads == kWThreads, "the fused kernel runs E, W and POST with one block size");
+
+struct FusedSmem {
+    union U {
+        WSmemT<kStages> w;       // ring + its mbarriers (the barriers lie beyond the other two members)
+        PostScratch sc;
+        ESmem es;
+    } u;
+    __align__(16) EmSlot st;
+    RefitAcc tmp[kFThreads / 32];    // per-warp staging of the M-step sums before they are shipped to CTA 0
+    int idx, flag;
+    long long mark[8];
+};
+static_assert(sizeof(PostScratch) <= offsetof(WSmemT<kStages>, full), "POST scratch must not reach the ring's barriers");
+static_assert(sizeof(ESmem) <= offsetof(WSmemT<kStages>, full), "E scratch must not reach the ring's barriers");
+static_assert(sizeof(FusedSmem) <= 113 * 1024, "two CTAs per SM");
+
+__device__ __forceinline__ uint32_t em_cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t em_ld_dsmem_u32(const void* local, uint32_t rank) {
+    uint32_t addr = em_smem_u32(local), remote, v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(rank));
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
+    return v;
+}
+__device__ __forceinline__ void em_st_dsmem_f64(double* local, uint32_t rank, double v) {
+    uint32_t addr = em_smem_u32(local), remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+}
+__device__ __forceinline__ void em_st_dsmem_u32(void* local, uint32_t rank, uint32_t v) {
+    uint32_t addr = em_smem_u32(local), remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(rank));
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(v) : "memory");
+}
+
+// E6 for slab t of one image by ONE CTA: the chunk ranges a cluster of em_wmat CTAs would share are run one
+// after the other and their partial sums added in the same (rank) order, so w is bit-identical to em_wmat's.
+template <int kSt>
+__device__ void wmat_slab(WSmemT<kSt>& sm, const Img& im, int N, int M, int t, int& ring, uint64_t policy, bool keep,
+                          uint64_t keep_policy, double bias, bool stream) {
+    const int tid = threadIdx.x;
+    const int nchunks = (N + kJR - 1) / kJR, passes = (M + kMP - 1) / kMP, cs = wmat_split(N);
+    const double* slab = im.lsim + (size_t)t * N * kTK;
+    double* red = &sm.a[0][0];
+    double* part = &sm.b[0][0];
+    for (int pass = 0; pass < passes; ++pass) {
+        int G, R;
+        wpass_shape(M, pass, G, R);
+        const int ws = G * R;
+        const double* wtp = im.wt + (size_t)pass * N * kMP;
+        for (int r = 0; r < cs; ++r) {
+            int c0 = 0, c1 = 0;
+            if (stream) { c0 = (int)((long long)nchunks * r / cs); c1 = (int)((long long)nchunks * (r + 1) / cs); }
+            switch (R) {
+            case 4: wmat_pass<4, kSt>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, keep, red, part); break;
+            case 8: wmat_pass<8, kSt>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, keep, red, part); break;
+            case 12: wmat_pass<12, kSt>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, keep, red, part); break;
+            default: wmat_pass<16, kSt>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, keep, red, part); break;
+            }
+            __syncthreads();                                         // the partial sums of this range are complete
+            for (int e = tid; e < ws * kTK; e += kFThreads) {
+                const int mm = e / kTK, col = e % kTK, k = t * kTK + col, m = pass * kMP + mm;
+                if (k < N && m < M) {
+                    double* dst = im.w + (size_t)m * N + k;
+                    // running sum of the ranges parked in the output element itself (this thread owns it)
+                    const double sum = r == 0 ? part[e] : *dst + part[e];
+                    if (r + 1 < cs) *dst = sum;
+                    else em_st_keep(dst, wmat_finish(im.wt[(size_t)pass * N * kMP + (size_t)k * ws + mm], im.lweight[k], im.colsum[k], sum, bias),
+                                    keep_policy);
+                }
+            }
+            // the ring (generic-proxy writes of red / part) is refilled by the async proxy next
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+        }
+    }
+}
+
+// M-step sums (refit_sums) of hypothesis rows spread over the warps of the whole cluster; results land in the
+// RefitAcc array of CTA 0 (distributed shared memory).  Only for the plain M-step phase.
+__device__ void fused_presum(FusedSmem& S, const Img& im, int N, int M, uint32_t rank, uint32_t C, const Team& T) {
+    RefitAcc* acc0 = refit_acc(S.u.sc);                              // same offset in every CTA
+    RefitAcc* s_tmp = S.tmp;
+    const int gw = (int)rank * T.nwarps + T.warp, tw = (int)C * T.nwarps;
+    for (int m = gw; m < M; m += tw) {
+        refit_sums(im, im.w + (size_t)m * N, nullptr, -1, m, -1, s_tmp[T.warp], T);
+        __syncwarp();
+        // ship the accumulator to CTA 0, 4 bytes per lane and round
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&s_tmp[T.warp]);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&acc0[m]);
+        for (int i = T.lane; i < (int)(sizeof(RefitAcc) / 4); i += 32) em_st_dsmem_u32(dst + i, 0, src[i]);
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(kFThreads, 2) em_fused_kernel(EmParams P, int max_steps, int keep) {
+    extern __shared__ __align__(128) unsigned char f_smem_raw[];
+    FusedSmem& S = *reinterpret_cast<FusedSmem*>(f_smem_raw);
+    const Team T = make_team();
+    const int tid = T.tid;
+    const uint32_t rank = em_cluster_ctarank(), C = em_cluster_nctarank();
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            em_mbar_init(em_smem_u32(&S.u.w.full[s]), 1);
+            em_mbar_init(em_smem_u32(&S.u.w.empty[s]), kFThreads / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (auto& m : S.mark) m = 0;
+    }
+    __syncthreads();
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    const uint64_t keep_policy = em_policy_keep();
+    const bool stream = P.cfg.use_weights != 0;
+    const double bias = P.cfg.wbias;
+    int ring = 0;                                    // position in the bulk-copy ring, carried over slabs, supersteps and images
+    long long t_mark = 0;
+    auto mark = [&](int k) {                          // cycles of CTA 0 per phase (profiling runs)
+        if (P.stats && rank == 0 && tid == 0) { const long long c = clock64(); S.mark[k] += c - t_mark; t_mark = c; }
+    };
+    for (;;) {
+        if (rank == 0 && tid == 0) S.idx = atomicAdd(P.ctl + 6, 1);
+        em_cluster_sync();
+        const int slot = (int)em_ld_dsmem_u32(&S.idx, 0);
+        em_cluster_sync();                           // CTA 0 may overwrite idx only after every CTA has read it
+        if (slot >= P.n_slots) break;
+        copy_slot(&S.st, P.slots + slot, T);         // every CTA: the state em_init left in HBM
+        __syncthreads();
+        const int N = S.st.N;
+        const Img im = make_img(N, P.ws + S.st.ws_off, P.segs + 4 * (size_t)S.st.base);
+        const int ntile = (N + 31) / 32, tiles = (N + kTK - 1) / kTK;
+        int steps = 0;
+        if (P.stats && rank == 0 && tid == 0) t_mark = clock64();
+        while (!S.st.done) {                         // identical in every CTA of the cluster
+            const int M = S.st.M;
+            // ---- E ----------------------------------------------------------------------------
+            estep_load_constants(S.u.es, S.st);
+            __syncthreads();
+            for (int b = (int)rank; b < ntile; b += (int)C) estep_tile(S.u.es, im, N, M, b * 32, keep_policy);
+            // wt is read through the async proxy (bulk copies) by the other CTAs
+            asm volatile("fence.proxy.async;" ::: "memory");
+            mark(0);
+            em_cluster_sync();
+            mark(1);
+            // ---- W ----------------------------------------------------------------------------
+            asm volatile("fence.proxy.async;" ::: "memory");
+            for (int t = (int)rank; t < tiles; t += (int)C)
+                wmat_slab<kStages>(S.u.w, im, N, M, t, ring, policy, keep != 0, keep_policy, bias, stream);
+            mark(2);
+            em_cluster_sync();
+            mark(3);
+            // ---- POST -------------------------------------------------------------------------
+            const bool presum = S.st.phase == PH_MSTEP && P.cfg.do_iterations && C > 1;
+            if (presum) {
+                fused_presum(S, im, N, M, rank, C, T);
+                em_cluster_sync();
+            }
+            mark(4);
+            if (rank == 0) {
+                if (P.stats && tid == 0) {
+                    atomicAdd(P.stats + 0, (unsigned long long)N * N * sizeof(double));
+                    atomicAdd(P.stats + 1, 2ull * M * N * N);
+                    atomicAdd(P.stats + 2, 1ull);
+                    atomicAdd(P.stats + 3, 8ull * (3ull * M * N + 5ull * N));
+                    atomicAdd(P.stats + 4, 8ull * (5ull * N + 3ull * M * N));
+                }
+                post_slot(S.st, S.u.sc, im, P.out, P.cfg, P.overflow, P.overflow_cap, P.ovlock, T, presum);
+                __syncthreads();
+                ++steps;
+                if (tid == 0 && steps >= max_steps && !S.st.done) { P.ctl[5] = 1; S.st.done = 1; }     // runaway guard
+            }
+            mark(5);
+            em_cluster_sync();
+            if (rank != 0) {
+                // mirror what E and W need: the header and the E-step constants
+                constexpr int kHead = (int)(offsetof(EmSlot, cur) / 4);
+                constexpr int kC0 = (int)(offsetof(EmSlot, pv) / 4), kC1 = (int)(offsetof(EmSlot, cw) / 4);
+                uint32_t* d = reinterpret_cast<uint32_t*>(&S.st);
+                for (int i = tid; i < kHead; i += kFThreads) d[i] = em_ld_dsmem_u32(d + i, 0);
+                for (int i = kC0 + tid; i < kC1; i += kFThreads) d[i] = em_ld_dsmem_u32(d + i, 0);
+            }
+            __syncthreads();
+            mark(6);
+        }
+        if (P.stats && rank == 0 && tid == 0) atomicMax(P.stats + 5, (unsigned long long)steps);
+    }
+    if (P.stats && rank == 0 && tid == 0)
+        for (int k = 0; k < 7; ++k) atomicAdd(P.stats + 8 + k, (unsigned long long)S.mark[k]);
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 // Device-driven loop: a CUDA graph of conditional WHILE nodes, one per tier of grid sizes
@@ -621,9 +848,11 @@ constexpr int kMaxGroups = 8;
 constexpr int kGroupSlots = 26;       // images per group (default; VPK_EM_GROUPS overrides the group count)
 
 struct GroupRun { EmParams P; cudaStream_t s; int n, nmax, csl, bound, step; bool done; };
+enum { MODE_FUSED = 0, MODE_GRAPH = 1, MODE_HOST = 2 };
 struct EmWave {
     bool begun = false;                    // wave_begin done, wave_run pending
     bool device_loop = true;
+    int mode = MODE_FUSED, cluster = 8, keep = 0;
     int begin = 0, end = 0, n = 0, G = 0;
     size_t budget = 0;
     std::vector<int32_t> order;
@@ -645,6 +874,8 @@ struct EmState {
     cudaEvent_t fork = nullptr, ready = nullptr;
     int last_supersteps = 0;
     unsigned long long totals[6] = {0, 0, 0, 0, 0, 0};   // accumulated W-product statistics + supersteps (profiling runs)
+    unsigned long long phase_cycles[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // fused kernel, CTA 0 of every cluster (profiling runs)
+    int max_clusters[17] = {};             // co-resident clusters of em_fused_kernel per cluster size (0 = not asked yet)
 };
 
 void em_free(vpk_ctx* ctx) {
@@ -771,11 +1002,27 @@ static int plan_wave(vpk_ctx* ctx, EmState* st, const EmParams& P0, const int32_
     // groups: the wave's images (heaviest first) are dealt round-robin, so every group gets the same
     // mix of sizes; a group's slots are contiguous.  One group per ~kGroupSlots images.
     static const int env_groups = getenv("VPK_EM_GROUPS") ? atoi(getenv("VPK_EM_GROUPS")) : 0;
-    const bool host_loop_env = getenv("VPK_EM_HOST_LOOP") != nullptr;     // read per call: smoke() toggles it
-    W.device_loop = !host_loop_env && !ctx->profiling;   // no per-kernel events inside a graph
+    // How the superstep loop runs (read per call: smoke() and the tests toggle it):
+    //   fused (default) : one persistent kernel, a cluster per image (em_fused_kernel)
+    //   graph           : E / W / POST kernels in a CUDA graph of conditional WHILE nodes, several groups in flight;
+    //                     chosen by itself for a few very large images (one cluster per image would leave the GPU idle)
+    //   host            : the same three kernels launched by the host (VPK_EM_HOST_LOOP=1)
+    const char* mode_env = getenv("VPK_EM_MODE");
+    const char* cl_env = getenv("VPK_EM_CLUSTER");
+    int cluster = cl_env ? atoi(cl_env) : (nmax > 3072 ? 16 : 8);
+    if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8 && cluster != 16) cluster = 8;
+    int mode = MODE_FUSED;
+    if (getenv("VPK_EM_HOST_LOOP")) mode = MODE_HOST;
+    else if (mode_env && !strcmp(mode_env, "graph")) mode = MODE_GRAPH;
+    else if (mode_env && !strcmp(mode_env, "host")) mode = MODE_HOST;
+    else if (!mode_env && nmax > 1536 && (long long)n * cluster * 4 < (long long)ctx->num_sms) mode = MODE_GRAPH;
+    if (mode == MODE_GRAPH && ctx->profiling) mode = MODE_HOST;      // no per-kernel events inside a graph
+    W.mode = mode; W.cluster = cluster;
+    W.device_loop = mode == MODE_GRAPH;
     int G = env_groups > 0 ? env_groups : (n + kGroupSlots - 1) / kGroupSlots;
     G = std::max(1, std::min(G, std::min(n, kMaxGroups)));
-    if (ctx->profiling) G = 1;          // per-kernel events are recorded on the context's stream
+    if (ctx->profiling || mode == MODE_FUSED) G = 1;   // per-kernel events are recorded on the context's stream; the fused
+                                                       // kernel takes the images from one queue, heaviest first
     EmParams P;
     memcpy(&P, &P0, sizeof(EmParams));
     P.slots = st->slots.as<EmSlot>(); P.desc = st->desc.as<SlotDesc>(); P.ws = st->ws.as<double>();
@@ -854,6 +1101,41 @@ static int wave_run(vpk_ctx* ctx, EmState* st) {
             em_init_kernel<<<r.n, kInitThreads, 0, r.s>>>(r.P);
             VPK_TRY(check_launch("em_init"));
         }
+        if (W.mode == MODE_FUSED) {
+            const int C = W.cluster;
+            if (!st->max_clusters[C]) {
+                cudaLaunchConfig_t oc = {};
+                oc.gridDim = dim3(C * 64); oc.blockDim = dim3(kFThreads); oc.dynamicSmemBytes = sizeof(FusedSmem);
+                cudaLaunchAttribute oa[1];
+                oa[0].id = cudaLaunchAttributeClusterDimension;
+                oa[0].val.clusterDim.x = C; oa[0].val.clusterDim.y = 1; oa[0].val.clusterDim.z = 1;
+                oc.attrs = oa; oc.numAttrs = 1;
+                int nc = 0;
+                VPK_CUDA(cudaOccupancyMaxActiveClusters(&nc, em_fused_kernel, &oc));
+                if (nc <= 0) { set_error("vpk_em: a cluster of %d CTAs of em_fused_kernel does not fit this device", C); return VPK_ERR_STATE; }
+                st->max_clusters[C] = nc;
+            }
+            const int nclusters = std::max(1, std::min(r.n, st->max_clusters[C]));
+            // similarity matrices of the images in flight (the heaviest ones come first) within 60 % of the L2: default
+            // cache policy, they stay resident from one superstep to the next (evict-first otherwise)
+            double inflight = 0.0;
+            const SlotDesc* hd = st->h_desc.as<SlotDesc>();
+            for (int i = 0; i < nclusters; ++i) inflight += 8.0 * hd[i].N * hd[i].N;
+            W.keep = inflight <= 0.6 * (double)ctx->l2_bytes ? 1 : 0;
+            KernelScope ks(ctx, "em_fused");
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(nclusters * C);
+            lc.blockDim = dim3(kFThreads);
+            lc.dynamicSmemBytes = sizeof(FusedSmem);
+            lc.stream = r.s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            lc.attrs = at; lc.numAttrs = 1;
+            VPK_CUDA(cudaLaunchKernelEx(&lc, em_fused_kernel, r.P, max_steps, W.keep));
+            VPK_TRY(check_launch("em_fused"));
+            VPK_CUDA(join(g));
+        }
         if (W.device_loop) {
             EmLoopGraph& L = *st->loop[g];
             if (!L.exec || L.n != r.n || L.nmax != r.nmax || memcmp(&L.key, &r.P, sizeof(EmParams)) != 0) {
@@ -865,7 +1147,11 @@ static int wave_run(vpk_ctx* ctx, EmState* st) {
         }
     }
     int steps = 0;
-    if (W.device_loop) {
+    if (W.mode == MODE_FUSED) {
+        VPK_CUDA(cudaMemcpyAsync(h_cnt, W.P.ctl, kCtlInts * sizeof(int), cudaMemcpyDeviceToHost, sm));
+        VPK_CUDA(cudaStreamSynchronize(sm));
+        if (h_cnt[5]) { set_error("vpk_em: supersteps did not terminate"); return VPK_ERR_STATE; }
+    } else if (W.device_loop) {
         VPK_CUDA(cudaMemcpyAsync(h_cnt, W.P.ctl, G * kCtlInts * sizeof(int), cudaMemcpyDeviceToHost, sm));
         VPK_CUDA(cudaStreamSynchronize(sm));
         for (int g = 0; g < G; ++g) {
@@ -908,14 +1194,20 @@ static int wave_run(vpk_ctx* ctx, EmState* st) {
     }
     if (trace) {
         const auto t_end = std::chrono::steady_clock::now();
-        fprintf(stderr, "[vpk_em] wave n=%d groups=%d %s loop, graphs rebuilt=%d, supersteps %d, %.3f ms\n", W.n, G,
-                W.device_loop ? "device" : "host", rebuilt, steps, std::chrono::duration<double, std::milli>(t_end - t_begin).count());
+        fprintf(stderr, "[vpk_em] wave n=%d groups=%d %s, cluster=%d keep=%d, graphs rebuilt=%d, supersteps %d, %.3f ms\n", W.n, G,
+                W.mode == MODE_FUSED ? "fused kernel" : (W.device_loop ? "device loop" : "host loop"), W.cluster, W.keep, rebuilt, steps,
+                std::chrono::duration<double, std::milli>(t_end - t_begin).count());
     }
     st->last_supersteps = steps;
     if (W.P.stats) {
-        unsigned long long h[5] = {0, 0, 0, 0, 0};
-        VPK_CUDA(cudaMemcpy(h, W.P.stats, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        unsigned long long h[16] = {};
+        VPK_CUDA(cudaMemcpy(h, W.P.stats, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         for (int k = 0; k < 3; ++k) st->totals[k] += h[k];
+        if (W.mode == MODE_FUSED) {
+            steps = (int)h[5];                                   // supersteps of the slowest image
+            st->last_supersteps = steps;
+            for (int k = 0; k < 7; ++k) st->phase_cycles[k] += h[8 + k];
+        }
         st->totals[3] += (unsigned long long)steps;
         st->totals[4] += h[3];
         st->totals[5] += h[4];
@@ -944,6 +1236,8 @@ int em_dev(vpk_ctx* ctx, const double* d_lines, const double* d_segments, const 
     if (!st->attr_set) {
         VPK_CUDA(cudaFuncSetAttribute(em_wmat_kernel<kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WSmemT<kStages>)));
         VPK_CUDA(cudaFuncSetAttribute(em_wmat_kernel<kStagesTail>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WSmemT<kStagesTail>)));
+        VPK_CUDA(cudaFuncSetAttribute(em_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
+        VPK_CUDA(cudaFuncSetAttribute(em_fused_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         for (auto& ev : st->gdone) VPK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& r : st->gev) for (auto& ev : r) VPK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         VPK_CUDA(cudaEventCreateWithFlags(&st->fork, cudaEventDisableTiming));
@@ -1019,6 +1313,13 @@ int vpk_em_stats(vpk_ctx* ctx, uint64_t out[6], int reset) {
     if (!ctx || !out) { set_error("vpk_em_stats: bad argument"); return VPK_ERR_ARG; }
     for (int k = 0; k < 6; ++k) out[k] = ctx->em ? ctx->em->totals[k] : 0;
     if (reset && ctx->em) for (auto& t : ctx->em->totals) t = 0;
+    return VPK_OK;
+}
+
+int vpk_em_phase_cycles(vpk_ctx* ctx, uint64_t out[8], int reset) {
+    if (!ctx || !out) { set_error("vpk_em_phase_cycles: bad argument"); return VPK_ERR_ARG; }
+    for (int k = 0; k < 8; ++k) out[k] = ctx->em ? ctx->em->phase_cycles[k] : 0;
+    if (reset && ctx->em) for (auto& t : ctx->em->phase_cycles) t = 0;
     return VPK_OK;
 }
 

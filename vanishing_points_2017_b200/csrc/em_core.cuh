@@ -1421,8 +1421,10 @@ VPK_DEVFN bool init_slot(EmSlot& st, InitScratch& isc, const Img& im, const EmOu
 // the reference's control flow until the next E-step is needed or the image is
 // finished.
 // ---------------------------------------------------------------------------
+// presummed: the entry phase is PH_MSTEP and the caller has already filled refit_acc(sc)[0 .. M) with the sums
+// of refit_sums (the fused kernel spreads them over the warps of a whole cluster).
 VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut& out, const vpk_em_config& cfg,
-                         double* big, size_t big_cap, int* big_lock, const Team& T) {
+                         double* big, size_t big_cap, int* big_lock, const Team& T, bool presummed = false) {
     const int N = im.N;
     const double max_stdd = 1e-6;            // angle mode (:197)
     int ph = st.phase;
@@ -1466,7 +1468,8 @@ VPK_DEVFN void post_slot(EmSlot& st, PostScratch& sc, const Img& im, const EmOut
             RefitAcc* acc = refit_acc(sc);
             if (cfg.do_iterations) {
                 VPK_MARK(sc, T, 1);
-                for (int m = T.warp; m < M; m += T.nwarps) refit_sums(im, im.w + (size_t)m * N, nullptr, -1, m, -1, acc[m], T);
+                if (!presummed)
+                    for (int m = T.warp; m < M; m += T.nwarps) refit_sums(im, im.w + (size_t)m * N, nullptr, -1, m, -1, acc[m], T);
                 team_sync();
                 VPK_MARK(sc, T, 2);
                 refit_finish(acc, M, im, im.w, (size_t)N, nullptr, false, sc.flag2, T);
