@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kPairThreads) em_pair_kernel(EmParams P) {
                     knn_insert(s_kd + tid, s_kj + tid, kPairThreads, cnt, d2, j);
                 }
             }
-            slab[(size_t)j * kTK + col] = val;
+            slab[(size_t)j * kTK + lsim_swz(j, col)] = val;
             part += val;
         }
     }
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kInitThreads) em_init_kernel(EmParams P) {
 struct ESmem {
     double c_pv[kMaxM], c_vx[kMaxM], c_vy[kMaxM], c_inv2s[kMaxM], c_coef[kMaxM];
     double s_pl[kEThreads / 32][32];
-    double s_wt[kMaxM / kMP][32][kMP + 1];       // +1: conflict-free column writes
+    double s_wt[kMaxM / kMP][32][kMP + 1];       // +1: conflict-free column writes (rows of a pass: 8 * tiles <= kMP)
 };
 
 // the constants of the E-step on the slot's selected VP set (prepare_estep) -> shared memory
@@ -319,7 +319,7 @@ __device__ __forceinline__ void estep_tile(ESmem& es, const Img& im, int N, int 
 #pragma unroll
     for (int mi = 0; mi < kMI; ++mi) {
         const int m = warp + NW * mi, p = m / kMP, mm = m % kMP;
-        if (p < passes && mm < wpass_stride(M, p)) {
+        if (p < passes && mm < 8 * wpass_tiles(M, p)) {
             double x = 0.0;
             if (m < M) {
                 x = plv[mi] * es.c_pv[m] * inv_pl;                      // calc_pvl (:128)
@@ -332,9 +332,9 @@ __device__ __forceinline__ void estep_tile(ESmem& es, const Img& im, int N, int 
     __syncthreads();
     const int nl = min(32, N - n0);
     for (int p = 0; p < passes; ++p) {
-        const int ws = wpass_stride(M, p);
-        double* dst = im.wt + (size_t)p * N * kMP + (size_t)n0 * ws;
-        for (int e = tid; e < nl * ws; e += kEThreads) em_st_keep(dst + e, es.s_wt[p][e / ws][e % ws], keep);
+        const int ws = wpass_stride(M, p), rows = ws - 4;                  // the 4 padding doubles of a line are never read
+        double* dst = im.wt + (size_t)p * N * kMPS + (size_t)n0 * ws;
+        for (int e = tid; e < nl * rows; e += kEThreads) em_st_keep(dst + (size_t)(e / rows) * ws + (e % rows), es.s_wt[p][e / rows][e % rows], keep);
     }
 }
 
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(kEThreads) em_estep_kernel(EmParams P) {
 template <int STAGES>
 struct WSmemT {
     double a[STAGES][kJR * kTK];           // lsim rows
-    double b[STAGES][kJR * kMP];           // wt rows; reused for the per-CTA partial result (kMP x kTK)
+    double b[STAGES][kJR * kMPS];          // wt rows; b[0..1] reused for the per-CTA partial result (kMP x kTK)
     unsigned long long full[STAGES], empty[STAGES];
 };
 
@@ -404,18 +404,25 @@ __device__ __forceinline__ double em_ld_dsmem(const double* local, uint32_t rank
     return v;
 }
 
-// main loop of one pass for R VP rows per thread: chunks [c0, c1) of the slab
-template <int R, int kStages>
+// D (8 x 8) += A (8 x 4, row) * B (4 x 8, col) on the FP64 tensor-core path.  Lane l = 4 g + t holds A[g][t], B[t][g]
+// and D[g][2t], D[g][2t + 1].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// main loop of one pass of MT 8-row tiles of VP rows: chunks [c0, c1) of the slab.  The (8 MT x 32)(32 x 64) product
+// of a chunk runs on the FP64 tensor cores: warp w takes the 16 columns 16 (w & 3) .. and the row half (w >> 2) of the
+// chunk, i.e. 4 k-steps x MT x 2 instructions.  The fragments are read straight from the bulk-copied rows (both
+// layouts are bank-conflict free, see lsim_swz / wpass_stride).  The two row halves are added (first + second) at the
+// end; the result lands in part[row * 64 + column].
+template <int MT, int kStages>
 __device__ __forceinline__ void wmat_pass(WSmemT<kStages>& sm, const double* slab, const double* wtp, int ws, int N, int c0, int c1,
-                                          int G, int& ring, uint64_t policy, bool keep, double* red, double* part) {
+                                          int& ring, uint64_t policy, bool keep, double* red, double* part) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int NWARP = kWThreads / 32;
-    const int wpg = NWARP / G;                       // warps per group
-    const int g = warp / wpg, wg = warp % wpg;
-    const int rpw = kJR / wpg;                       // rows per warp per chunk
-    double acc[R][2];
+    const int g = lane >> 2, t = lane & 3, wn = warp & 3, wk = warp >> 2;
+    double acc[MT][2][2];
 #pragma unroll
-    for (int m = 0; m < R; ++m) acc[m][0] = acc[m][1] = 0.0;
+    for (int m = 0; m < MT; ++m) acc[m][0][0] = acc[m][0][1] = acc[m][1][0] = acc[m][1][1] = 0.0;
     const int nch = c1 - c0;
     int next_issue = 0;                              // warp 0 only
     auto issue = [&](int i) {                        // chunk c0 + i into ring slot (ring + i) % kStages
@@ -426,6 +433,7 @@ __device__ __forceinline__ void wmat_pass(WSmemT<kStages>& sm, const double* sla
         else em_bulk_g2s_hint(em_smem_u32(sm.a[s]), slab + (size_t)j0 * kTK, (uint32_t)(jn * kTK * sizeof(double)), bar, policy);
         em_bulk_g2s(em_smem_u32(sm.b[s]), wtp + (size_t)j0 * ws, (uint32_t)(jn * ws * sizeof(double)), bar);
     };
+    const int colb0 = (16 * wn + g) ^ (t << 2), colb1 = (16 * wn + 8 + g) ^ (t << 2);
     for (int i = 0; i < nch; ++i) {
         const int pos = ring + i, s = pos % kStages;
         if (warp == 0) {
@@ -445,31 +453,33 @@ __device__ __forceinline__ void wmat_pass(WSmemT<kStages>& sm, const double* sla
         }
         em_mbar_wait(em_smem_u32(&sm.full[s]), (uint32_t)((pos / kStages) & 1));
         const int jn = min(kJR, N - (c0 + i) * kJR);
-        auto row_fma = [&](int r) {
-            const double2 a2 = *reinterpret_cast<const double2*>(&sm.a[s][r * kTK + 2 * lane]);
-            const double2* b2 = reinterpret_cast<const double2*>(&sm.b[s][r * ws + g * R]);
-#pragma unroll
-            for (int q = 0; q < R / 2; ++q) {
-                const double2 bb = b2[q];
-                acc[2 * q][0] = fma(bb.x, a2.x, acc[2 * q][0]);
-                acc[2 * q][1] = fma(bb.x, a2.y, acc[2 * q][1]);
-                acc[2 * q + 1][0] = fma(bb.y, a2.x, acc[2 * q + 1][0]);
-                acc[2 * q + 1][1] = fma(bb.y, a2.y, acc[2 * q + 1][1]);
-            }
-        };
+        const double* Bs = sm.a[s];
+        const double* As = sm.b[s];
         if (jn == kJR) {
-            // full chunk: no per-row predicate, so the loads of the next row can be hoisted over the FMAs
-            if (G == 1) {
 #pragma unroll
-                for (int rr = 0; rr < kJR / NWARP; ++rr) row_fma(wg * (kJR / NWARP) + rr);
-            } else {
+            for (int ks = 0; ks < kJR / 8; ++ks) {
+                const int j = (kJR / 2) * wk + 4 * ks + t;
+                const double b0 = Bs[j * kTK + colb0], b1 = Bs[j * kTK + colb1];
 #pragma unroll
-                for (int rr = 0; rr < 2 * kJR / NWARP; ++rr) row_fma(wg * (2 * kJR / NWARP) + rr);
+                for (int m = 0; m < MT; ++m) {
+                    const double a = As[j * ws + 8 * m + g];
+                    dmma884(acc[m][0][0], acc[m][0][1], a, b0);
+                    dmma884(acc[m][1][0], acc[m][1][1], a, b1);
+                }
             }
         } else {
-            for (int rr = 0; rr < rpw; ++rr) {
-                const int r = wg * rpw + rr;
-                if (r < jn) row_fma(r);
+            // last chunk of the image: rows >= jn are stale shared memory and must not contribute
+#pragma unroll
+            for (int ks = 0; ks < kJR / 8; ++ks) {
+                const int j = (kJR / 2) * wk + 4 * ks + t;
+                const bool ok = j < jn;
+                const double b0 = ok ? Bs[j * kTK + colb0] : 0.0, b1 = ok ? Bs[j * kTK + colb1] : 0.0;
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    const double a = ok ? As[j * ws + 8 * m + g] : 0.0;
+                    dmma884(acc[m][0][0], acc[m][0][1], a, b0);
+                    dmma884(acc[m][1][0], acc[m][1][1], a, b1);
+                }
             }
         }
         __syncwarp();
@@ -477,17 +487,15 @@ __device__ __forceinline__ void wmat_pass(WSmemT<kStages>& sm, const double* sla
     }
     ring += nch;
     __syncthreads();                                 // every warp has finished reading the ring
-    // cross-warp reduction in the (now idle) a-ring: red[warp][r][col]
+    // the two row halves of the chunks, in the (now idle) ring: first half -> part, second half -> red
+    double* dst = wk ? red : part;
 #pragma unroll
-    for (int m = 0; m < R; ++m)
-        *reinterpret_cast<double2*>(&red[(warp * 16 + m) * kTK + 2 * lane]) = make_double2(acc[m][0], acc[m][1]);
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+            *reinterpret_cast<double2*>(&dst[(8 * m + g) * kTK + 16 * wn + 8 * n + 2 * t]) = make_double2(acc[m][n][0], acc[m][n][1]);
     __syncthreads();
-    for (int e = tid; e < G * R * kTK; e += kWThreads) {
-        const int mm = e / kTK, col = e % kTK, gg = mm / R, r = mm % R;
-        double sum = 0.0;
-        for (int w = 0; w < wpg; ++w) sum += red[((gg * wpg + w) * 16 + r) * kTK + col];
-        part[e] = sum;
-    }
+    for (int e = tid; e < 8 * MT * kTK; e += kWThreads) part[e] = part[e] + red[e];
 }
 
 // keep: the similarity matrices of the slots still active fit the L2, so they are loaded with the
@@ -536,25 +544,23 @@ __global__ void __launch_bounds__(kWThreads, 2) em_wmat_kernel(EmParams P, int c
     if (stream && rank < cs) { c0 = (int)((long long)nchunks * rank / cs); c1 = (int)((long long)nchunks * (rank + 1) / cs); }
     int ring = 0;                                   // ring position, carries over passes
     for (int pass = 0; pass < passes; ++pass) {
-        int G, R;
-        wpass_shape(M, pass, G, R);
-        const int ws = G * R;
-        const double* wtp = im.wt + (size_t)pass * N * kMP;
-        switch (R) {
-        case 4: wmat_pass<4, kStages>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, keep != 0, red, part); break;
-        case 8: wmat_pass<8, kStages>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, keep != 0, red, part); break;
-        case 12: wmat_pass<12, kStages>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, keep != 0, red, part); break;
-        default: wmat_pass<16, kStages>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, keep != 0, red, part); break;
+        const int mt = wpass_tiles(M, pass), ws = 8 * mt + 4;
+        const double* wtp = im.wt + (size_t)pass * N * kMPS;
+        switch (mt) {
+        case 1: wmat_pass<1, kStages>(sm, slab, wtp, ws, N, c0, c1, ring, policy, keep != 0, red, part); break;
+        case 2: wmat_pass<2, kStages>(sm, slab, wtp, ws, N, c0, c1, ring, policy, keep != 0, red, part); break;
+        case 3: wmat_pass<3, kStages>(sm, slab, wtp, ws, N, c0, c1, ring, policy, keep != 0, red, part); break;
+        default: wmat_pass<4, kStages>(sm, slab, wtp, ws, N, c0, c1, ring, policy, keep != 0, red, part); break;
         }
         if (csl > 1) em_cluster_sync(); else __syncthreads();          // partial results are complete
         if (rank == 0) {
-            for (int e = tid; e < ws * kTK; e += kWThreads) {
+            for (int e = tid; e < 8 * mt * kTK; e += kWThreads) {
                 const int mm = e / kTK, col = e % kTK, k = t * kTK + col, m = pass * kMP + mm;
                 if (k < N && m < M) {
                     double sum = part[e];
                     for (int r = 1; r < cs; ++r) sum += em_ld_dsmem(part + e, (uint32_t)r);
                     em_st_keep(im.w + (size_t)m * N + k,
-                               wmat_finish(im.wt[(size_t)pass * N * kMP + (size_t)k * ws + mm], im.lweight[k], im.colsum[k], sum, bias),
+                               wmat_finish(im.wt[(size_t)pass * N * kMPS + (size_t)k * ws + mm], im.lweight[k], im.colsum[k], sum, bias),
                                keep_policy);
                 }
             }
@@ -678,28 +684,26 @@ __device__ void wmat_slab(WSmemT<kSt>& sm, const Img& im, int N, int M, int t, i
     double* red = &sm.a[0][0];
     double* part = &sm.b[0][0];
     for (int pass = 0; pass < passes; ++pass) {
-        int G, R;
-        wpass_shape(M, pass, G, R);
-        const int ws = G * R;
-        const double* wtp = im.wt + (size_t)pass * N * kMP;
+        const int mt = wpass_tiles(M, pass), ws = 8 * mt + 4;
+        const double* wtp = im.wt + (size_t)pass * N * kMPS;
         for (int r = 0; r < cs; ++r) {
             int c0 = 0, c1 = 0;
             if (stream) { c0 = (int)((long long)nchunks * r / cs); c1 = (int)((long long)nchunks * (r + 1) / cs); }
-            switch (R) {
-            case 4: wmat_pass<4, kSt>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, keep, red, part); break;
-            case 8: wmat_pass<8, kSt>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, keep, red, part); break;
-            case 12: wmat_pass<12, kSt>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, keep, red, part); break;
-            default: wmat_pass<16, kSt>(sm, slab, wtp, ws, N, c0, c1, G, ring, policy, keep, red, part); break;
+            switch (mt) {
+            case 1: wmat_pass<1, kSt>(sm, slab, wtp, ws, N, c0, c1, ring, policy, keep, red, part); break;
+            case 2: wmat_pass<2, kSt>(sm, slab, wtp, ws, N, c0, c1, ring, policy, keep, red, part); break;
+            case 3: wmat_pass<3, kSt>(sm, slab, wtp, ws, N, c0, c1, ring, policy, keep, red, part); break;
+            default: wmat_pass<4, kSt>(sm, slab, wtp, ws, N, c0, c1, ring, policy, keep, red, part); break;
             }
             __syncthreads();                                         // the partial sums of this range are complete
-            for (int e = tid; e < ws * kTK; e += kFThreads) {
+            for (int e = tid; e < 8 * mt * kTK; e += kFThreads) {
                 const int mm = e / kTK, col = e % kTK, k = t * kTK + col, m = pass * kMP + mm;
                 if (k < N && m < M) {
                     double* dst = im.w + (size_t)m * N + k;
                     // running sum of the ranges parked in the output element itself (this thread owns it)
                     const double sum = r == 0 ? part[e] : *dst + part[e];
                     if (r + 1 < cs) *dst = sum;
-                    else em_st_keep(dst, wmat_finish(im.wt[(size_t)pass * N * kMP + (size_t)k * ws + mm], im.lweight[k], im.colsum[k], sum, bias),
+                    else em_st_keep(dst, wmat_finish(im.wt[(size_t)pass * N * kMPS + (size_t)k * ws + mm], im.lweight[k], im.colsum[k], sum, bias),
                                     keep_policy);
                 }
             }
@@ -798,8 +802,17 @@ __global__ void __launch_bounds__(kFThreads, 2) em_fused_kernel(EmParams P, int 
                     atomicAdd(P.stats + 3, 8ull * (3ull * M * N + 5ull * N));
                     atomicAdd(P.stats + 4, 8ull * (5ull * N + 3ull * M * N));
                 }
+#if defined(VPK_EM_MARKS)
+                if (tid == 0) { for (auto& m : S.u.sc.mark) m = 0; S.u.sc.mark_t = clock64(); }
+#endif
                 post_slot(S.st, S.u.sc, im, P.out, P.cfg, P.overflow, P.overflow_cap, P.ovlock, T, presum);
                 __syncthreads();
+#if defined(VPK_EM_MARKS)
+                if (P.stats && tid == 0) {
+                    for (int k = 0; k < 10; ++k) atomicAdd(P.stats + 16 + k, (unsigned long long)S.u.sc.mark[k]);
+                    atomicAdd(P.stats + 26, 1ull);
+                }
+#endif
                 ++steps;
                 if (tid == 0 && steps >= max_steps && !S.st.done) { P.ctl[5] = 1; S.st.done = 1; }     // runaway guard
             }
@@ -1213,7 +1226,7 @@ static int wave_run(vpk_ctx* ctx, EmState* st) {
         st->totals[5] += h[4];
 #if defined(VPK_EM_MARKS)
         unsigned long long mk[11];
-        VPK_CUDA(cudaMemcpy(mk, W.P.stats + 8, 11 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        VPK_CUDA(cudaMemcpy(mk, W.P.stats + (W.mode == MODE_FUSED ? 16 : 8), 11 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         fprintf(stderr, "[vpk_em] POST cycles per slot-superstep (%llu):", mk[10]);
         for (int k = 0; k < 10; ++k) fprintf(stderr, " m%d=%.0f", k, (double)mk[k] / (double)std::max<unsigned long long>(mk[10], 1));
         fprintf(stderr, "\n");

@@ -48,7 +48,8 @@ constexpr int kMaxM = VPK_MAX_VP;
 constexpr int kMaxComp = 100;              // probability_functions.py:87
 constexpr int kCells = VPK_GRID * VPK_GRID;
 constexpr int kTK = 64;                    // columns per similarity slab (W kernel tile)
-constexpr int kMP = 32;                    // VP rows per weight-matrix pass (two groups of <= 16)
+constexpr int kMP = 32;                    // VP rows per weight-matrix pass (up to four 8-row tensor-core tiles)
+constexpr int kMPS = kMP + 4;              // largest row stride of the W operand wt (8 * tiles + 4 doubles: conflict-free fragments)
 constexpr int kPostThreads = 512;
 constexpr int kK1 = 10;                    // kNN rating: nearest by distance (vp_localisation.py:34)
 constexpr double kPi = 3.141592653589793;
@@ -160,31 +161,36 @@ struct Img {
     double* pvl;           // (kMaxM,N)
     double* w;             // (kMaxM,N)
     double* wt;            // pvl*lweight, the A operand of the W kernel: pass p (VP rows 32p..32p+31) at
-                           // wt + p*N*32, line n of the pass at stride wpass_stride(M, p) (rows padded with zeros)
+                           // wt + p*N*kMPS, line n of the pass at stride wpass_stride(M, p) (rows padded with zeros)
     size_t scratch_cap;    // doubles available from lvsq on
 };
 
 VPK_HD size_t lsim_doubles(int N) { return (size_t)((N + kTK - 1) / kTK) * kTK * (size_t)N; }
-VPK_HD size_t lsim_index(int N, int j, int k) { return ((size_t)(k / kTK) * N + j) * kTK + (k % kTK); }
-// Shape of pass p of the weight-matrix product for M hypotheses: G groups of warps, R VP rows per
-// thread (R in {4, 8, 12, 16}); the pass covers G*R >= rows-in-pass VP rows.
-VPK_HD void wpass_shape(int M, int p, int& G, int& R) {
+// Element (j,k) of the similarity matrix: 64-column slabs, each N x 64 contiguous; inside a row the column is
+// XOR-swizzled with the row index (bits 2-3) so that the FP64 tensor-core B fragments of the W kernel (4 rows x 8
+// columns per instruction, read straight from the bulk-copied rows) hit 16 different shared-memory bank pairs.
+VPK_HD int lsim_swz(int j, int col) { return col ^ ((j & 3) << 2); }
+VPK_HD size_t lsim_index(int N, int j, int k) { return ((size_t)(k / kTK) * N + j) * kTK + lsim_swz(j, k % kTK); }
+// Pass p of the weight-matrix product for M hypotheses covers the VP rows 32p .. 32p+31 as wpass_tiles() tiles of
+// 8 rows (m8n8k4 FP64 mma); line n of the pass stores its 8 * tiles operands (rows >= M are zeros) at a stride
+// of 8 * tiles + 4 doubles (= 4 mod 8: the A fragments are conflict-free too).
+VPK_HD int wpass_tiles(int M, int p) {
     int mp = M - p * kMP;
     if (mp > kMP) mp = kMP;
-    G = mp > 16 ? 2 : 1;
-    R = ((mp + G - 1) / G + 3) & ~3;
-    if (R < 4) R = 4;
+    if (mp < 1) mp = 1;
+    return (mp + 7) / 8;
 }
-VPK_HD int wpass_stride(int M, int p) { int G, R; wpass_shape(M, p, G, R); return G * R; }
+VPK_HD int wpass_stride(int M, int p) { return 8 * wpass_tiles(M, p) + 4; }
 VPK_HD size_t wt_index(int N, int n, int m, int M) {
     const int p = m / kMP;
-    return (size_t)p * N * kMP + (size_t)n * wpass_stride(M, p) + (m % kMP);
+    return (size_t)p * N * kMPS + (size_t)n * wpass_stride(M, p) + (m % kMP);
 }
 VPK_HD size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 VPK_HD size_t slot_doubles(int N) {
     size_t n = (size_t)N;
-    return align16(lsim_doubles(N)) + align16(3 * n) + 3 * align16(n) + align16((n + 1) / 2 + 1) + 4 * align16((size_t)kMaxM * n) + 16;
+    return align16(lsim_doubles(N)) + align16(3 * n) + 3 * align16(n) + align16((n + 1) / 2 + 1) + 3 * align16((size_t)kMaxM * n) +
+           align16((size_t)(kMaxM / kMP) * kMPS * n) + 16;
 }
 
 VPK_DEV Img make_img(int N, double* ws, const double* lp) {
@@ -201,8 +207,8 @@ VPK_DEV Img make_img(int N, double* ws, const double* lp) {
     im.lvsq = p; p += align16((size_t)kMaxM * n);
     im.pvl = p; p += align16((size_t)kMaxM * n);
     im.w = p; p += align16((size_t)kMaxM * n);
-    im.wt = p; p += align16((size_t)kMaxM * n);
-    im.scratch_cap = 4 * align16((size_t)kMaxM * n);
+    im.wt = p; p += align16((size_t)(kMaxM / kMP) * kMPS * n);
+    im.scratch_cap = 3 * align16((size_t)kMaxM * n) + align16((size_t)(kMaxM / kMP) * kMPS * n);
     return im;
 }
 
@@ -759,8 +765,8 @@ VPK_DEV void estep_line(const Img& im, int M, const double* pv, const double* vx
     const double lw = im.lweight[n];
     const int passes = (M + kMP - 1) / kMP;
     for (int p = 0; p < passes; ++p) {
-        const int ws = wpass_stride(M, p);
-        for (int mm = 0; mm < ws; ++mm) {
+        const int rows = 8 * wpass_tiles(M, p);
+        for (int mm = 0; mm < rows; ++mm) {
             const int m = p * kMP + mm;
             double x = 0.0;
             if (m < M) {
