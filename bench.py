@@ -419,6 +419,8 @@ def run_ours(args, rank, world, local_rank):
                 elif kname == "em_wmat":
                     # 8 N^2 bytes of similarity matrix per per-image product (counted on the device)
                     byt = em_stats["wmat_bytes"] / max(k["launches"], 1)
+                elif kname == "em_poste":
+                    byt = (em_stats["post_bytes"] + em_stats["estep_bytes"]) / max(k["launches"], 1)
                 elif kname == "em_post":
                     byt = em_stats["post_bytes"] / max(k["launches"], 1)
                 elif kname == "em_estep":

@@ -13,17 +13,19 @@
 //               W kernel streams contiguous memory), its column sums, and the
 //               kNN line rating (E4) from the same distances.
 //   em_init   : once per image: unit lines, prior mixture, initial VPs (E0-E2).
-//   superstep : em_estep (CTA = 32 lines of an image; E5) ->
-//               em_wmat  (CTA = (image, slab): the (M x N)(N x N) weight-matrix
-//                         product E6, lsim streamed by bulk async copies through
-//                         a 4-stage shared-memory ring, FP64 FMA) ->
-//               em_post  (CTA = image: reductions over the lines, 3x3
-//                         eigen-solves, prune / split / merge / convergence
-//                         decisions E7-E12, choice of the next superstep).
-//   The images of a wave are dealt to groups; every group runs its supersteps on its own
-//   stream, driven by a device-side loop (CUDA graph of conditional WHILE nodes) or, for
-//   profiling, by the host (chunks of supersteps, the active count read three chunks behind),
-//   so that the latency-bound POST of one group overlaps the HBM-bound W of the others.
+//   superstep : em_wmat  (CTA = (image, slab): the (M x N)(N x N) weight-matrix
+//                         product E6 on the FP64 tensor cores, lsim streamed by bulk
+//                         async copies through a 4-stage shared-memory ring) ->
+//               em_poste (CLUSTER of 4 CTAs = image: reductions over the lines spread
+//                         over the cluster, 3x3 eigen-solves, prune / split / merge /
+//                         convergence decisions E7-E12 in the leading CTA, then the
+//                         E-step E5 of the next superstep on all CTAs).
+//   The superstep loop runs in one of three forms (plan_wave): the images of a wave dealt to groups, every
+//   group driven by a device-side loop (CUDA graph of conditional WHILE nodes) on its own stream, so that
+//   the latency-bound POST of one group overlaps the tensor/HBM-bound W of the others (default); the same
+//   kernels launched by the host (profiling, VPK_EM_HOST_LOOP=1); or ONE persistent kernel with a cluster
+//   per image that keeps the slot state in shared memory from the first E-step to the result (em_fused,
+//   VPK_EM_MODE=fused).  All three produce bit-identical results.
 //
 // Arithmetic is float64 throughout: the reference is float64, its discrete
 // decisions (counts < 3, argmax, err > 1.5, angle < thresh) sit on float values
@@ -207,12 +209,13 @@ __global__ void __launch_bounds__(kPairThreads) em_pair_kernel(EmParams P) {
 // arrive compacts the flags into list `next` IN SLOT ORDER (slots are sorted heaviest image first, so the
 // CTAs of the big images of the next E / W launches start first) and returns the number of active slots
 // to its thread 0 (-1 in every other CTA).  Block-wide; thread 0 of the last CTA resets the ticket.
-__device__ int close_slot_list(const EmParams& P, int next, const Team& T) {
+__device__ int close_slot_list(const EmParams& P, int next, const Team& T, int participants = -1) {
     __shared__ int s_last, s_warp[32], s_base;
+    if (participants < 0) participants = (int)gridDim.x;
     __syncthreads();
     if (T.tid == 0) {
         __threadfence();
-        s_last = atomicAdd(P.ctl + 4, 1) == (int)gridDim.x - 1;
+        s_last = atomicAdd(P.ctl + 4, 1) == participants - 1;
         s_base = 0;
     }
     __syncthreads();
@@ -274,10 +277,11 @@ __global__ void __launch_bounds__(kInitThreads) em_init_kernel(EmParams P) {
 // warp order; the W operand tile is staged in shared memory and written with
 // contiguous stores.
 // ---------------------------------------------------------------------------
+constexpr int kEL = 64;                      // lines per E-step tile
 struct ESmem {
     double c_pv[kMaxM], c_vx[kMaxM], c_vy[kMaxM], c_inv2s[kMaxM], c_coef[kMaxM];
-    double s_pl[kEThreads / 32][32];
-    double s_wt[kMaxM / kMP][32][kMP + 1];       // +1: conflict-free column writes (rows of a pass: 8 * tiles <= kMP)
+    double s_pl[8][kEL];
+    double s_wt[kMaxM / kMP][kEL][kMP + 1];      // +1: conflict-free column writes (rows of a pass: 8 * tiles <= kMP)
 };
 
 // the constants of the E-step on the slot's selected VP set (prepare_estep) -> shared memory
@@ -287,38 +291,41 @@ __device__ __forceinline__ void estep_load_constants(ESmem& es, const EmSlot& st
     }
 }
 
-// E5 for lines n0 .. n0+31 of one image (block-wide, kEThreads threads; es.c_* loaded and synchronised)
+// E5 for lines n0 .. n0+63 of one image (block-wide, kEThreads = 256 threads; es.c_* loaded and synchronised).
+// Thread (line = tid & 63, q = tid >> 6) evaluates the VP rows m = q, q + 4, q + 8, ...; the per-line normaliser
+// p(l) is the sum of eight partials -- rows m = r (mod 8), r = 0 .. 7, in that order -- whatever the tiling.
 __device__ __forceinline__ void estep_tile(ESmem& es, const Img& im, int N, int M, int n0, uint64_t keep) {
-    constexpr int NW = kEThreads / 32, kMI = kMaxM / NW;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n = n0 + lane;
+    constexpr int NQ = kEThreads / kEL, kMI = kMaxM / NQ;      // 4 row classes per line, 16 rows per thread
+    const int tid = threadIdx.x, q = tid / kEL, ln = tid % kEL;
+    const int n = n0 + ln;
     const bool live = n < N;
     const LineGeom g = line_geom(im.lp, live ? n : 0);
     double plv[kMI];
-    double part = 0.0;
+    double part[2] = {0.0, 0.0};                               // rows m = q (mod 8) and m = q + 4 (mod 8)
 #pragma unroll
     for (int mi = 0; mi < kMI; ++mi) {
-        const int m = warp + NW * mi;
+        const int m = q + NQ * mi;
         plv[mi] = 0.0;
         if (m < M) {
             double lvsq;
             estep_nm(g, es.c_vx[m], es.c_vy[m], es.c_inv2s[m], es.c_coef[m], lvsq, plv[mi]);
             if (live) em_st_keep(im.lvsq + (size_t)m * N + n, lvsq, keep);
-            part += plv[mi] * es.c_pv[m];
+            part[mi & 1] += plv[mi] * es.c_pv[m];
         }
     }
-    es.s_pl[warp][lane] = part;
+    es.s_pl[q][ln] = part[0];
+    es.s_pl[q + NQ][ln] = part[1];
     __syncthreads();
     double pl = 0.0;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) pl += es.s_pl[w][lane];
+    for (int w = 0; w < 8; ++w) pl += es.s_pl[w][ln];
     if (pl < 1e-12) pl = 1e-12;                                         // :117 (NaN stays NaN)
     const double inv_pl = 1.0 / pl;
     const double lw = live ? im.lweight[n] : 0.0;
     const int passes = (M + kMP - 1) / kMP;
 #pragma unroll
     for (int mi = 0; mi < kMI; ++mi) {
-        const int m = warp + NW * mi, p = m / kMP, mm = m % kMP;
+        const int m = q + NQ * mi, p = m / kMP, mm = m % kMP;
         if (p < passes && mm < 8 * wpass_tiles(M, p)) {
             double x = 0.0;
             if (m < M) {
@@ -326,11 +333,11 @@ __device__ __forceinline__ void estep_tile(ESmem& es, const Img& im, int N, int 
                 if (live) em_st_keep(im.pvl + (size_t)m * N + n, x, keep);
                 x *= lw;                                                // weight_matrix :517
             }
-            es.s_wt[p][lane][mm] = x;
+            es.s_wt[p][ln][mm] = x;
         }
     }
     __syncthreads();
-    const int nl = min(32, N - n0);
+    const int nl = min(kEL, N - n0);
     for (int p = 0; p < passes; ++p) {
         const int ws = wpass_stride(M, p), rows = ws - 4;                  // the 4 padding doubles of a line are never read
         double* dst = im.wt + (size_t)p * N * kMPS + (size_t)n0 * ws;
@@ -345,7 +352,7 @@ __global__ void __launch_bounds__(kEThreads) em_estep_kernel(EmParams P) {
     const int slot = P.lists[cur * P.n_slots + blockIdx.y];
     const EmSlot& st = P.slots[slot];
     if (!st.run_e) return;
-    const int N = st.N, M = st.M, n0 = blockIdx.x * 32;
+    const int N = st.N, M = st.M, n0 = blockIdx.x * kEL;
     if (n0 >= N) return;
     // algorithmic bytes of this slot's E-step: segments + line weights in, the planes lvsq, pvl, wt out
     if (P.stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.stats + 4, 8ull * (5ull * N + 3ull * M * N));
@@ -573,49 +580,6 @@ __global__ void __launch_bounds__(kWThreads, 2) em_wmat_kernel(EmParams P, int c
 }
 
 // ---------------------------------------------------------------------------
-// em_post: one CTA per active slot
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPostThreads) em_post_kernel(EmParams P, TierCtl tc) {
-    __shared__ __align__(16) EmSlot st;
-    __shared__ PostScratch sc;
-    const int step = P.ctl[3], cur = step & 1;
-    const Team T = make_team();
-#if defined(VPK_EM_MARKS)
-    if (T.tid == 0) { for (auto& m : sc.mark) m = 0; sc.mark_t = clock64(); }
-#endif
-    if ((int)blockIdx.x < P.ctl[cur]) {
-        const int slot = P.lists[cur * P.n_slots + blockIdx.x];
-        copy_slot(&st, P.slots + slot, T);
-        __syncthreads();
-        // algorithmic bytes of this slot's POST: the planes w, lvsq, pvl and the unit lines + weights once
-        if (P.stats && T.tid == 0) atomicAdd(P.stats + 3, 8ull * (3ull * st.M * st.N + 5ull * st.N));
-        const Img im = make_img(st.N, P.ws + st.ws_off, P.segs + 4 * (size_t)st.base);
-        post_slot(st, sc, im, P.out, P.cfg, P.overflow, P.overflow_cap, P.ovlock, T);
-        __syncthreads();
-        VPK_MARK(sc, T, 6);
-        copy_slot(P.slots + slot, &st, T);
-        if (T.tid == 0) P.alive[slot] = st.done ? 0 : 1;
-        __syncthreads();
-        VPK_MARK(sc, T, 7);
-#if defined(VPK_EM_MARKS)
-        if (P.stats && T.tid == 0) {
-            for (int k = 0; k < 10; ++k) atomicAdd(P.stats + 8 + k, (unsigned long long)sc.mark[k]);
-            atomicAdd(P.stats + 18, 1ull);
-        }
-#endif
-    }
-    // the last block to finish closes the superstep: the other list becomes current, this one is emptied
-    const int live = close_slot_list(P, cur ^ 1, T);
-    if (live >= 0) {
-        P.ctl[cur] = 0;
-        P.ctl[3] = step + 1;
-        const bool stop = step + 1 >= tc.max_steps;
-        if (stop && live > 0) P.ctl[5] = 1;
-        for (int j = 0; j < tc.n; ++j) cudaGraphSetConditional(tc.h[j], (!stop && live > tc.thr[j]) ? 1u : 0u);
-    }
-}
-
-// ---------------------------------------------------------------------------
 // em_fused: the whole superstep loop of an image inside ONE persistent kernel.
 //
 // A thread-block cluster owns an image from its first E-step to its result: the
@@ -716,9 +680,8 @@ __device__ void wmat_slab(WSmemT<kSt>& sm, const Img& im, int N, int M, int t, i
 
 // M-step sums (refit_sums) of hypothesis rows spread over the warps of the whole cluster; results land in the
 // RefitAcc array of CTA 0 (distributed shared memory).  Only for the plain M-step phase.
-__device__ void fused_presum(FusedSmem& S, const Img& im, int N, int M, uint32_t rank, uint32_t C, const Team& T) {
-    RefitAcc* acc0 = refit_acc(S.u.sc);                              // same offset in every CTA
-    RefitAcc* s_tmp = S.tmp;
+__device__ void cluster_presum(RefitAcc* acc0, RefitAcc* s_tmp, const Img& im, int N, int M, uint32_t rank, uint32_t C, const Team& T) {
+    // acc0: the RefitAcc array of the POST scratch (same shared-memory offset in every CTA of the cluster)
     const int gw = (int)rank * T.nwarps + T.warp, tw = (int)C * T.nwarps;
     for (int m = gw; m < M; m += tw) {
         refit_sums(im, im.w + (size_t)m * N, nullptr, -1, m, -1, s_tmp[T.warp], T);
@@ -766,7 +729,7 @@ __global__ void __launch_bounds__(kFThreads, 2) em_fused_kernel(EmParams P, int 
         __syncthreads();
         const int N = S.st.N;
         const Img im = make_img(N, P.ws + S.st.ws_off, P.segs + 4 * (size_t)S.st.base);
-        const int ntile = (N + 31) / 32, tiles = (N + kTK - 1) / kTK;
+        const int ntile = (N + kEL - 1) / kEL, tiles = (N + kTK - 1) / kTK;
         int steps = 0;
         if (P.stats && rank == 0 && tid == 0) t_mark = clock64();
         while (!S.st.done) {                         // identical in every CTA of the cluster
@@ -774,7 +737,7 @@ __global__ void __launch_bounds__(kFThreads, 2) em_fused_kernel(EmParams P, int 
             // ---- E ----------------------------------------------------------------------------
             estep_load_constants(S.u.es, S.st);
             __syncthreads();
-            for (int b = (int)rank; b < ntile; b += (int)C) estep_tile(S.u.es, im, N, M, b * 32, keep_policy);
+            for (int b = (int)rank; b < ntile; b += (int)C) estep_tile(S.u.es, im, N, M, b * kEL, keep_policy);
             // wt is read through the async proxy (bulk copies) by the other CTAs
             asm volatile("fence.proxy.async;" ::: "memory");
             mark(0);
@@ -790,7 +753,7 @@ __global__ void __launch_bounds__(kFThreads, 2) em_fused_kernel(EmParams P, int 
             // ---- POST -------------------------------------------------------------------------
             const bool presum = S.st.phase == PH_MSTEP && P.cfg.do_iterations && C > 1;
             if (presum) {
-                fused_presum(S, im, N, M, rank, C, T);
+                cluster_presum(refit_acc(S.u.sc), S.tmp, im, N, M, rank, C, T);
                 em_cluster_sync();
             }
             mark(4);
@@ -836,6 +799,94 @@ __global__ void __launch_bounds__(kFThreads, 2) em_fused_kernel(EmParams P, int 
 }
 
 // ---------------------------------------------------------------------------
+// em_poste: POST of superstep s and the E-step of superstep s + 1 of every active slot in one launch, one
+// CLUSTER of kPC CTAs per slot: the line sweeps of the M-step (one warp per hypothesis) are spread over the warps
+// of the whole cluster, CTA 0 runs the state machine (post_slot) on the slot state in its shared memory, the other
+// CTAs mirror the new E-step constants through distributed shared memory and all of them share the E-step tiles.
+// Replaces em_post + em_estep in the kernel-per-phase loops: a superstep is W -> POSTE (two launches, not three).
+// ---------------------------------------------------------------------------
+struct PosteSmem {
+    union U {
+        PostScratch sc;
+        ESmem es;
+    } u;
+    __align__(16) EmSlot st;
+    RefitAcc tmp[kFThreads / 32];
+};
+
+__global__ void __launch_bounds__(kFThreads) em_poste_kernel(EmParams P, TierCtl tc) {
+    extern __shared__ __align__(128) unsigned char p_smem_raw[];
+    PosteSmem& S = *reinterpret_cast<PosteSmem*>(p_smem_raw);
+    const Team T = make_team();
+    const int tid = T.tid;
+    const uint32_t rank = em_cluster_ctarank(), C = em_cluster_nctarank();
+    const int cid = (int)(blockIdx.x / C);
+    const int step = P.ctl[3], cur = step & 1;
+    const int n_active = P.ctl[cur];
+    // every CTA of the cluster has read the control words before its leading CTA can take part in closing the
+    // superstep (the closing CTA rewrites them)
+    em_cluster_sync();
+    if (cid < n_active) {                                          // uniform over the cluster
+        const int slot = P.lists[cur * P.n_slots + cid];
+        copy_slot(&S.st, P.slots + slot, T);
+        __syncthreads();
+        const int N = S.st.N, M = S.st.M;
+        const Img im = make_img(N, P.ws + S.st.ws_off, P.segs + 4 * (size_t)S.st.base);
+        const bool presum = S.st.phase == PH_MSTEP && P.cfg.do_iterations && C > 1;
+        if (presum) {
+            cluster_presum(refit_acc(S.u.sc), S.tmp, im, N, M, rank, C, T);
+            em_cluster_sync();
+        }
+        if (rank == 0) {
+            if (P.stats && tid == 0) atomicAdd(P.stats + 3, 8ull * (3ull * M * N + 5ull * N));
+#if defined(VPK_EM_MARKS)
+            if (tid == 0) { for (auto& m : S.u.sc.mark) m = 0; S.u.sc.mark_t = clock64(); }
+#endif
+            post_slot(S.st, S.u.sc, im, P.out, P.cfg, P.overflow, P.overflow_cap, P.ovlock, T, presum);
+            __syncthreads();
+#if defined(VPK_EM_MARKS)
+            if (P.stats && tid == 0) {
+                for (int k = 0; k < 10; ++k) atomicAdd(P.stats + 8 + k, (unsigned long long)S.u.sc.mark[k]);
+                atomicAdd(P.stats + 18, 1ull);
+            }
+#endif
+            copy_slot(P.slots + slot, &S.st, T);                   // the W kernel and the next POSTE read the state from HBM
+            if (tid == 0) P.alive[slot] = S.st.done ? 0 : 1;
+        }
+        em_cluster_sync();
+        if (rank != 0) {
+            constexpr int kHead = (int)(offsetof(EmSlot, cur) / 4);
+            constexpr int kC0 = (int)(offsetof(EmSlot, pv) / 4), kC1 = (int)(offsetof(EmSlot, cw) / 4);
+            uint32_t* d = reinterpret_cast<uint32_t*>(&S.st);
+            for (int i = tid; i < kHead; i += kFThreads) d[i] = em_ld_dsmem_u32(d + i, 0);
+            for (int i = kC0 + tid; i < kC1; i += kFThreads) d[i] = em_ld_dsmem_u32(d + i, 0);
+        }
+        __syncthreads();
+        em_cluster_sync();                                         // CTA 0 keeps its shared memory until everybody has read it
+        // ---- E-step of the next superstep on the VP set POST selected
+        if (!S.st.done && S.st.run_e) {
+            const int M2 = S.st.M, ntile = (N + kEL - 1) / kEL;
+            if (P.stats && rank == 0 && tid == 0) atomicAdd(P.stats + 4, 8ull * (5ull * N + 3ull * M2 * N));
+            estep_load_constants(S.u.es, S.st);
+            __syncthreads();
+            const uint64_t keep = em_policy_keep();
+            for (int b = (int)rank; b < ntile; b += (int)C) estep_tile(S.u.es, im, N, M2, b * kEL, keep);
+        }
+    }
+    // the last leading CTA to finish POST closes the superstep: the other list becomes current, this one is emptied
+    if (rank == 0) {
+        const int live = close_slot_list(P, cur ^ 1, T, (int)(gridDim.x / C));
+        if (live >= 0) {
+            P.ctl[cur] = 0;
+            P.ctl[3] = step + 1;
+            const bool stop = step + 1 >= tc.max_steps;
+            if (stop && live > 0) P.ctl[5] = 1;
+            for (int j = 0; j < tc.n; ++j) cudaGraphSetConditional(tc.h[j], (!stop && live > tc.thr[j]) ? 1u : 0u);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 // Device-driven loop: a CUDA graph of conditional WHILE nodes, one per tier of grid sizes
@@ -858,6 +909,7 @@ struct EmLoopGraph {
 // loop on its own stream: POST (one CTA per image, latency bound) of one group overlaps the W product
 // (HBM bound) of the others, and a group's tail of slow images does not hold the other groups back.
 constexpr int kMaxGroups = 8;
+constexpr int kPosteCluster = 4;      // CTAs per image of em_poste (408 CTAs for the 102 images of the YUD batch: one wave)
 constexpr int kGroupSlots = 26;       // images per group (default; VPK_EM_GROUPS overrides the group count)
 
 struct GroupRun { EmParams P; cudaStream_t s; int n, nmax, csl, bound, step; bool done; };
@@ -912,11 +964,6 @@ static int enqueue_superstep(vpk_ctx* ctx, cudaStream_t sm, const EmParams& P, i
                              bool scoped) {
     const int tiles = (nmax + kTK - 1) / kTK;
     {
-        KernelScope ks(ctx, "em_estep", scoped);
-        em_estep_kernel<<<dim3((nmax + 31) / 32, bound), kEThreads, 0, sm>>>(P);
-        VPK_TRY(check_launch("em_estep"));
-    }
-    {
         KernelScope ks(ctx, "em_wmat", scoped);
         cudaLaunchConfig_t lc = {};
         lc.gridDim = dim3(tiles * csl, bound);
@@ -935,11 +982,29 @@ static int enqueue_superstep(vpk_ctx* ctx, cudaStream_t sm, const EmParams& P, i
         VPK_TRY(check_launch("em_wmat"));
     }
     {
-        KernelScope ks(ctx, "em_post", scoped);
-        em_post_kernel<<<bound, kPostThreads, 0, sm>>>(P, tc);
-        VPK_TRY(check_launch("em_post"));
+        KernelScope ks(ctx, "em_poste", scoped);
+        static const int pc_env = getenv("VPK_EM_POSTE_CLUSTER") ? atoi(getenv("VPK_EM_POSTE_CLUSTER")) : 0;
+        const int pc = (pc_env == 1 || pc_env == 2 || pc_env == 4 || pc_env == 8) ? pc_env : kPosteCluster;
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(bound * pc);
+        lc.blockDim = dim3(kFThreads);
+        lc.dynamicSmemBytes = sizeof(PosteSmem);
+        lc.stream = sm;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = pc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        VPK_CUDA(cudaLaunchKernelEx(&lc, em_poste_kernel, P, tc));
+        VPK_TRY(check_launch("em_poste"));
     }
     return VPK_OK;
+}
+
+// the E-step of the first superstep (every later one is the tail of em_poste)
+static int enqueue_first_estep(vpk_ctx* ctx, cudaStream_t sm, const EmParams& P, int n, int nmax) {
+    KernelScope ks(ctx, "em_estep");
+    em_estep_kernel<<<dim3((nmax + kEL - 1) / kEL, n), kEThreads, 0, sm>>>(P);
+    return check_launch("em_estep");
 }
 
 static int build_loop_graph(vpk_ctx* ctx, cudaStream_t sm, EmLoopGraph& G, const EmParams& P, int n, int nmax, int max_steps) {
@@ -1016,19 +1081,18 @@ static int plan_wave(vpk_ctx* ctx, EmState* st, const EmParams& P0, const int32_
     // mix of sizes; a group's slots are contiguous.  One group per ~kGroupSlots images.
     static const int env_groups = getenv("VPK_EM_GROUPS") ? atoi(getenv("VPK_EM_GROUPS")) : 0;
     // How the superstep loop runs (read per call: smoke() and the tests toggle it):
-    //   fused (default) : one persistent kernel, a cluster per image (em_fused_kernel)
-    //   graph           : E / W / POST kernels in a CUDA graph of conditional WHILE nodes, several groups in flight;
-    //                     chosen by itself for a few very large images (one cluster per image would leave the GPU idle)
-    //   host            : the same three kernels launched by the host (VPK_EM_HOST_LOOP=1)
+    //   graph (default) : W / POSTE kernels in a CUDA graph of conditional WHILE nodes, several groups in flight
+    //   host            : the same kernels launched by the host (VPK_EM_HOST_LOOP=1, profiling runs)
+    //   fused           : one persistent kernel, a cluster per image (em_fused_kernel, VPK_EM_MODE=fused): measured
+    //                     slower on full batches (the CTAs of a cluster idle while its leading CTA runs POST), see DESIGN.md
     const char* mode_env = getenv("VPK_EM_MODE");
     const char* cl_env = getenv("VPK_EM_CLUSTER");
     int cluster = cl_env ? atoi(cl_env) : (nmax > 3072 ? 16 : 8);
     if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8 && cluster != 16) cluster = 8;
-    int mode = MODE_FUSED;
+    int mode = MODE_GRAPH;
     if (getenv("VPK_EM_HOST_LOOP")) mode = MODE_HOST;
-    else if (mode_env && !strcmp(mode_env, "graph")) mode = MODE_GRAPH;
+    else if (mode_env && !strcmp(mode_env, "fused")) mode = MODE_FUSED;
     else if (mode_env && !strcmp(mode_env, "host")) mode = MODE_HOST;
-    else if (!mode_env && nmax > 1536 && (long long)n * cluster * 4 < (long long)ctx->num_sms) mode = MODE_GRAPH;
     if (mode == MODE_GRAPH && ctx->profiling) mode = MODE_HOST;      // no per-kernel events inside a graph
     W.mode = mode; W.cluster = cluster;
     W.device_loop = mode == MODE_GRAPH;
@@ -1149,6 +1213,7 @@ static int wave_run(vpk_ctx* ctx, EmState* st) {
             VPK_TRY(check_launch("em_fused"));
             VPK_CUDA(join(g));
         }
+        if (W.mode != MODE_FUSED) VPK_TRY(enqueue_first_estep(ctx, r.s, r.P, r.n, r.nmax));
         if (W.device_loop) {
             EmLoopGraph& L = *st->loop[g];
             if (!L.exec || L.n != r.n || L.nmax != r.nmax || memcmp(&L.key, &r.P, sizeof(EmParams)) != 0) {
@@ -1169,7 +1234,7 @@ static int wave_run(vpk_ctx* ctx, EmState* st) {
         VPK_CUDA(cudaStreamSynchronize(sm));
         for (int g = 0; g < G; ++g) {
             const int* c = h_cnt + g * kCtlInts;
-            ctx->launches += 3 * (int64_t)c[3];
+            ctx->launches += 2 * (int64_t)c[3];
             steps = std::max(steps, c[3]);
             if (c[5]) { set_error("vpk_em: supersteps did not terminate"); return VPK_ERR_STATE; }
         }
@@ -1250,6 +1315,7 @@ int em_dev(vpk_ctx* ctx, const double* d_lines, const double* d_segments, const 
         VPK_CUDA(cudaFuncSetAttribute(em_wmat_kernel<kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WSmemT<kStages>)));
         VPK_CUDA(cudaFuncSetAttribute(em_wmat_kernel<kStagesTail>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WSmemT<kStagesTail>)));
         VPK_CUDA(cudaFuncSetAttribute(em_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
+        VPK_CUDA(cudaFuncSetAttribute(em_poste_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PosteSmem)));
         VPK_CUDA(cudaFuncSetAttribute(em_fused_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         for (auto& ev : st->gdone) VPK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& r : st->gev) for (auto& ev : r) VPK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
