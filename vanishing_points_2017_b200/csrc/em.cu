@@ -13,13 +13,13 @@
 //               W kernel streams contiguous memory), its column sums, and the
 //               kNN line rating (E4) from the same distances.
 //   em_init   : once per image: unit lines, prior mixture, initial VPs (E0-E2).
-//   superstep : em_wmat  (CTA = (image, slab): the (M x N)(N x N) weight-matrix
+//   superstep : em_estep (CTA = 64 lines of an image; E5) ->
+//               em_wmat  (CTA = (image, slab): the (M x N)(N x N) weight-matrix
 //                         product E6 on the FP64 tensor cores, lsim streamed by bulk
 //                         async copies through a 4-stage shared-memory ring) ->
-//               em_poste (CLUSTER of 4 CTAs = image: reductions over the lines spread
-//                         over the cluster, 3x3 eigen-solves, prune / split / merge /
-//                         convergence decisions E7-E12 in the leading CTA, then the
-//                         E-step E5 of the next superstep on all CTAs).
+//               em_post  (CTA = image: reductions over the lines, 3x3
+//                         eigen-solves, prune / split / merge / convergence
+//                         decisions E7-E12, choice of the next superstep).
 //   The superstep loop runs in one of three forms (plan_wave): the images of a wave dealt to groups, every
 //   group driven by a device-side loop (CUDA graph of conditional WHILE nodes) on its own stream, so that
 //   the latency-bound POST of one group overlaps the tensor/HBM-bound W of the others (default); the same
@@ -580,6 +580,49 @@ __global__ void __launch_bounds__(kWThreads, 2) em_wmat_kernel(EmParams P, int c
 }
 
 // ---------------------------------------------------------------------------
+// em_post: one CTA per active slot
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPostThreads) em_post_kernel(EmParams P, TierCtl tc) {
+    __shared__ __align__(16) EmSlot st;
+    __shared__ PostScratch sc;
+    const int step = P.ctl[3], cur = step & 1;
+    const Team T = make_team();
+#if defined(VPK_EM_MARKS)
+    if (T.tid == 0) { for (auto& m : sc.mark) m = 0; sc.mark_t = clock64(); }
+#endif
+    if ((int)blockIdx.x < P.ctl[cur]) {
+        const int slot = P.lists[cur * P.n_slots + blockIdx.x];
+        copy_slot(&st, P.slots + slot, T);
+        __syncthreads();
+        // algorithmic bytes of this slot's POST: the planes w, lvsq, pvl and the unit lines + weights once
+        if (P.stats && T.tid == 0) atomicAdd(P.stats + 3, 8ull * (3ull * st.M * st.N + 5ull * st.N));
+        const Img im = make_img(st.N, P.ws + st.ws_off, P.segs + 4 * (size_t)st.base);
+        post_slot(st, sc, im, P.out, P.cfg, P.overflow, P.overflow_cap, P.ovlock, T);
+        __syncthreads();
+        VPK_MARK(sc, T, 6);
+        copy_slot(P.slots + slot, &st, T);
+        if (T.tid == 0) P.alive[slot] = st.done ? 0 : 1;
+        __syncthreads();
+        VPK_MARK(sc, T, 7);
+#if defined(VPK_EM_MARKS)
+        if (P.stats && T.tid == 0) {
+            for (int k = 0; k < 10; ++k) atomicAdd(P.stats + 8 + k, (unsigned long long)sc.mark[k]);
+            atomicAdd(P.stats + 18, 1ull);
+        }
+#endif
+    }
+    // the last block to finish closes the superstep: the other list becomes current, this one is emptied
+    const int live = close_slot_list(P, cur ^ 1, T);
+    if (live >= 0) {
+        P.ctl[cur] = 0;
+        P.ctl[3] = step + 1;
+        const bool stop = step + 1 >= tc.max_steps;
+        if (stop && live > 0) P.ctl[5] = 1;
+        for (int j = 0; j < tc.n; ++j) cudaGraphSetConditional(tc.h[j], (!stop && live > tc.thr[j]) ? 1u : 0u);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // em_fused: the whole superstep loop of an image inside ONE persistent kernel.
 //
 // A thread-block cluster owns an image from its first E-step to its result: the
@@ -959,10 +1002,23 @@ void em_free(vpk_ctx* ctx) {
     ctx->em = nullptr;
 }
 
+// VPK_EM_POSTE=1: a superstep is W -> POSTE (POST and the next E-step in one cluster-per-image kernel) instead of
+// E -> W -> POST.  Measured slower on full batches (its mostly idle CTAs compete with W for the SMs), kept for comparison.
+static bool use_poste() {
+    static const bool v = getenv("VPK_EM_POSTE") != nullptr;
+    return v;
+}
+
 // one superstep on the stream (direct launch or stream capture): E -> W -> POST over `bound` slots
 static int enqueue_superstep(vpk_ctx* ctx, cudaStream_t sm, const EmParams& P, int bound, int nmax, int csl, const TierCtl& tc,
                              bool scoped) {
     const int tiles = (nmax + kTK - 1) / kTK;
+    const bool poste = use_poste();
+    if (!poste) {
+        KernelScope ks(ctx, "em_estep", scoped);
+        em_estep_kernel<<<dim3((nmax + kEL - 1) / kEL, bound), kEThreads, 0, sm>>>(P);
+        VPK_TRY(check_launch("em_estep"));
+    }
     {
         KernelScope ks(ctx, "em_wmat", scoped);
         cudaLaunchConfig_t lc = {};
@@ -981,7 +1037,11 @@ static int enqueue_superstep(vpk_ctx* ctx, cudaStream_t sm, const EmParams& P, i
         else VPK_CUDA(cudaLaunchKernelEx(&lc, em_wmat_kernel<kStages>, P, csl, keep));
         VPK_TRY(check_launch("em_wmat"));
     }
-    {
+    if (!poste) {
+        KernelScope ks(ctx, "em_post", scoped);
+        em_post_kernel<<<bound, kPostThreads, 0, sm>>>(P, tc);
+        VPK_TRY(check_launch("em_post"));
+    } else {
         KernelScope ks(ctx, "em_poste", scoped);
         static const int pc_env = getenv("VPK_EM_POSTE_CLUSTER") ? atoi(getenv("VPK_EM_POSTE_CLUSTER")) : 0;
         const int pc = (pc_env == 1 || pc_env == 2 || pc_env == 4 || pc_env == 8) ? pc_env : kPosteCluster;
@@ -1213,7 +1273,7 @@ static int wave_run(vpk_ctx* ctx, EmState* st) {
             VPK_TRY(check_launch("em_fused"));
             VPK_CUDA(join(g));
         }
-        if (W.mode != MODE_FUSED) VPK_TRY(enqueue_first_estep(ctx, r.s, r.P, r.n, r.nmax));
+        if (W.mode != MODE_FUSED && use_poste()) VPK_TRY(enqueue_first_estep(ctx, r.s, r.P, r.n, r.nmax));
         if (W.device_loop) {
             EmLoopGraph& L = *st->loop[g];
             if (!L.exec || L.n != r.n || L.nmax != r.nmax || memcmp(&L.key, &r.P, sizeof(EmParams)) != 0) {
@@ -1234,7 +1294,7 @@ static int wave_run(vpk_ctx* ctx, EmState* st) {
         VPK_CUDA(cudaStreamSynchronize(sm));
         for (int g = 0; g < G; ++g) {
             const int* c = h_cnt + g * kCtlInts;
-            ctx->launches += 2 * (int64_t)c[3];
+            ctx->launches += (use_poste() ? 2 : 3) * (int64_t)c[3];
             steps = std::max(steps, c[3]);
             if (c[5]) { set_error("vpk_em: supersteps did not terminate"); return VPK_ERR_STATE; }
         }
