@@ -355,7 +355,7 @@ def run_ours(args, rank, world, local_rank):
         if args.strong and world > 1:
             # the path's only exchange: the per-image results of every shard end up on rank 0
             tg = time.perf_counter()
-            full = pipeline.gather_raw(out, idx, off, B_all, world, dist)
+            full = pipeline.gather_raw(out, off_all, world, rank, dist)
             gather_ms += (time.perf_counter() - tg) * 1e3
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps

@@ -88,7 +88,7 @@ def _worker_raw(rank, world, port, q):
     off_all = np.concatenate([[0], np.cumsum(n_all)])
     idx = pipeline.shard_batch(off_all, world, rank)
     arrs, off = _fake_raw(idx, n_all[idx])
-    out = pipeline.gather_raw(arrs, idx, off, len(n_all), world, dist)
+    out = pipeline.gather_raw(arrs, off_all, world, rank, dist)
     if rank == 0:
         q.put({k: v for k, v in out.items()})
     else:
@@ -116,7 +116,9 @@ def test_gather_raw_gloo_world2():
     np.testing.assert_array_equal(out["iterations"], np.arange(7) * 2)
     np.testing.assert_array_equal(out["vp"][:, 0, 0], np.arange(7.0))
     np.testing.assert_array_equal(out["vp_assoc"], np.repeat(np.arange(7), n_all))
-    # single rank: identity up to the image order
-    arrs, off = _fake_raw(np.array([2, 0, 1]), np.array([5, 3, 4]))
-    one = pipeline.gather_raw(arrs, np.array([2, 0, 1]), off, 3, 1)
+    np.testing.assert_array_equal(out["n_vp"], np.arange(7) % 5 + 1)
+    # single rank: the identity
+    arrs, off = _fake_raw(np.array([0, 1, 2]), np.array([3, 4, 5]))
+    one = pipeline.gather_raw(arrs, off, 1, 0)
     np.testing.assert_array_equal(one["vp_assoc"], np.repeat([0, 1, 2], [3, 4, 5]))
+    np.testing.assert_array_equal(one["vp"][:, 0, 1], np.arange(3) + 0.5)

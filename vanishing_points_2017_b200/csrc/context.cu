@@ -80,8 +80,6 @@ int vpk_destroy(vpk_ctx* ctx) {
     ctx->d_lines.release(); ctx->d_segments.release(); ctx->d_offsets.release(); ctx->d_work.release();
     ctx->d_hist.release(); ctx->d_img.release(); ctx->d_weights.release(); ctx->d_misc.release();
     ctx->h_stage.release();
-    for (auto& h : ctx->h_work) h.release();
-    for (auto& e : ctx->ev_work) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return VPK_OK;

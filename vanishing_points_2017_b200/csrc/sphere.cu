@@ -113,26 +113,106 @@ __device__ __forceinline__ bool intersection_cell(double ax, double ay, double a
     return true;
 }
 
-// One CTA per (image, tile_i, tile_j) work item of the upper-triangular pair
-// space.  Tiles are staged in shared memory as SoA (conflict-free for the
-// j-direction, broadcast for the i-direction).
+// ---- FP32 pre-binning ---------------------------------------------------------------------------------
+// The cell of an intersection is needed bit-exactly as the float64 expressions above give it, but a cell is
+// pi / S wide (6.3e-3 rad at S = 500) while float32 resolves ~1e-6 rad: the cell is computed in float32 together
+// with a rigorous bound of its own error, and only the pairs whose float32 position lies closer to a cell border
+// than that bound (a few per cent) are re-evaluated with the float64 expressions.  Error budget of the fast path:
+//   p = a x b from operands rounded to float32:   |dp_k| <= 2^-21 * mag,  mag = sum of the six |products|
+//   direction on the sphere:                      eps_s  <= 2 * 2^-21 * mag / |p| + 2^-21   (normalisation, rsqrt)
+//   beta  = asin(y):                              |dbeta|  <= eps_s / cos(beta) + 4e-7       (asinf: a few ulp of pi/2)
+//   alpha = asin(x / cos(beta)):                  |dalpha| <= eps_s (1/c + 1/c^2) / sqrt(1 - inner^2) + 4e-7
+//   index = angle * S / pi + S / 2 (float32):     1.5e-4 index units of rounding at magnitudes up to 512 (S <= 1024)
+// and everything is doubled once more.  Pairs near the poles or the alpha = +-pi/2 seam (c or sqrt(1 - inner^2)
+// below 0.05), degenerate pairs and images with S > 1024 always take the float64 path.
+__device__ __forceinline__ bool fast_cell(float ax, float ay, float az, float bx, float by, float bz, float s_over_pi,
+                                          float half_s, int S, int& row, int& col) {
+    const float t0 = ay * bz, t1 = az * by, t2 = az * bx, t3 = ax * bz, t4 = ax * by, t5 = ay * bx;
+    float px = t0 - t1, py = t2 - t3;
+    const float pz = t4 - t5;
+    const float mag = (fabsf(t0) + fabsf(t1)) + (fabsf(t2) + fabsf(t3)) + (fabsf(t4) + fabsf(t5));
+    const float n2 = px * px + py * py + pz * pz;
+    if (!(n2 > 1e-30f) || !(n2 < 1e30f)) return false;
+    const float rn = rsqrtf(n2);
+    if (pz < 0.0f) { px = -px; py = -py; }
+    const float y = py * rn, x = px * rn;
+    const float c2 = 1.0f - y * y;
+    if (!(c2 > 0.0025f)) return false;                       // cos(beta) < 0.05
+    const float rc = rsqrtf(c2);                             // 1 / cos(beta)
+    const float inner = x * rc;
+    const float q2 = 1.0f - inner * inner;
+    if (!(q2 > 0.0025f)) return false;
+    const float eps = 9.5367431640625e-7f * (mag * rn) + 4.76837158203125e-7f;          // 2^-20 mag / |p| + 2^-21
+    const float dbeta = eps * rc + 4e-7f;
+    const float dalpha = eps * (rc + rc * rc) * rsqrtf(q2) + 4e-7f;
+    const float fa = asinf(inner) * s_over_pi + half_s;      // angle_to_index + 0.5: the cell is floor(fa)
+    const float fb = asinf(y) * s_over_pi + half_s;
+    const float ma = 2.0f * (dalpha * s_over_pi + 1.5e-4f), mb = 2.0f * (dbeta * s_over_pi + 1.5e-4f);
+    const float ra = floorf(fa), rb = floorf(fb);
+    if (fa - ra < ma || ra + 1.0f - fa < ma || fb - rb < mb || rb + 1.0f - fb < mb) return false;
+    // away from the borders: the float64 cell is the same; the clip of angle_bin applies to both alike
+    col = min(max((int)ra, 0), S - 1);
+    row = (S - 1) - min(max((int)rb, 0), S - 1);
+    return true;
+}
+
+// Work list of the vote kernel, built on the device: item k = (image, tile_i, tile_j), tile_i <= tile_j, of the
+// upper-triangular tile-pair space of every image.  One block; images in chunks of blockDim.x with a running prefix.
+__global__ void sphere_items_kernel(const int32_t* __restrict__ offsets, int B, int4* __restrict__ work) {
+    __shared__ int s_warp[32], s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int b0 = 0; b0 < B; b0 += blockDim.x) {
+        const int b = b0 + threadIdx.x;
+        int T = 0;
+        if (b < B) T = (offsets[b + 1] - offsets[b] + kTile - 1) / kTile;
+        const int mine = T * (T + 1) / 2;
+        int incl = mine;
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        int k = before + incl - mine;
+        for (int ti = 0; ti < T; ++ti)
+            for (int tj = ti; tj < T; ++tj) work[k++] = make_int4(b, ti, tj, 0);
+        __syncthreads();
+        if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < nw; ++w) tot += s_warp[w]; s_base += tot; }
+        __syncthreads();
+    }
+}
+
+// One CTA per (image, tile_i, tile_j) work item.  Tiles are staged in shared memory as SoA, in float32 for the
+// fast path and float64 for the exact one.  Votes of a warp that fall into the same cell are merged
+// (__match_any_sync) before the integer atomic; pairs the fast path cannot decide are queued in shared memory and
+// evaluated in float64 afterwards by all threads (no divergence inside the pair loop).
+constexpr int kQueueCap = 4096;
 __global__ void __launch_bounds__(kVoteThreads)
 sphere_votes_kernel(const double* __restrict__ lines, const int32_t* __restrict__ offsets,
                     const int4* __restrict__ work, int S, const double* __restrict__ weights,
-                    uint32_t* __restrict__ hist, unsigned long long* __restrict__ whist) {
+                    uint32_t* __restrict__ hist, unsigned long long* __restrict__ whist, unsigned long long* __restrict__ stats) {
     __shared__ double sA[3][kTile], sB[3][kTile], sWA[kTile], sWB[kTile];
+    __shared__ float fA[3][kTile], fB[3][kTile];
+    __shared__ unsigned short s_queue[kQueueCap];
+    __shared__ int s_nq;
     const int4 item = work[blockIdx.x];
     const int b = item.x, ti = item.y, tj = item.z;
     const int base = offsets[b];
     const int N = offsets[b + 1] - base;
     const int i0 = ti * kTile, j0 = tj * kTile;
+    if (threadIdx.x == 0) s_nq = 0;
     for (int t = threadIdx.x; t < kTile; t += blockDim.x) {
         int gi = i0 + t, gj = j0 + t;
         bool vi = gi < N, vj = gj < N;
         const double* li = lines + 3 * (int64_t)(base + (vi ? gi : 0));
         const double* lj = lines + 3 * (int64_t)(base + (vj ? gj : 0));
-        sA[0][t] = li[0]; sA[1][t] = li[1]; sA[2][t] = li[2];
-        sB[0][t] = lj[0]; sB[1][t] = lj[1]; sB[2][t] = lj[2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double a = li[c], bb = lj[c];
+            sA[c][t] = a; sB[c][t] = bb;
+            fA[c][t] = (float)a; fB[c][t] = (float)bb;
+        }
         if (weights) {
             sWA[t] = weights[base + (vi ? gi : 0)];
             sWB[t] = weights[base + (vj ? gj : 0)];
@@ -141,22 +221,57 @@ sphere_votes_kernel(const double* __restrict__ lines, const int32_t* __restrict_
     __syncthreads();
     const double s = (double)S;
     const double half_over_s = __ddiv_rn(0.5, s);
+    const float s_over_pi = (float)(s / kPi), half_s = 0.5f * (float)S;
+    const bool fast_ok = S <= 1024;
     const int64_t plane = (int64_t)b * S * S;
     const int ni = min(kTile, N - i0), nj = min(kTile, N - j0);
-    for (int idx = threadIdx.x; idx < ni * kTile; idx += blockDim.x) {
-        int i = idx / kTile, j = idx % kTile;
-        if (j >= nj) continue;
-        if (i0 + i >= j0 + j) continue;           // i < j only
-        int row, col;
-        if (!intersection_cell(sA[0][i], sA[1][i], sA[2][i], sB[0][j], sB[1][j], sB[2][j], half_over_s, s, S, row, col))
-            continue;
-        int64_t cell = plane + (int64_t)row * S + col;
+    const int lane = threadIdx.x & 31;
+    auto vote = [&](bool valid, int row, int col, int i, int j) {
         if (weights) {
-            double q = floor(__dadd_rn(__dmul_rn(__dmul_rn(sWA[i], sWB[j]), 65536.0), 0.5));
-            if (q > 0.0) atomicAdd(whist + cell, (unsigned long long)q);
-        } else {
-            atomicAdd(hist + cell, 1u);
+            if (valid) {
+                double q = floor(__dadd_rn(__dmul_rn(__dmul_rn(sWA[i], sWB[j]), 65536.0), 0.5));
+                if (q > 0.0) atomicAdd(whist + plane + (int64_t)row * S + col, (unsigned long long)q);
+            }
+            return;
         }
+        // lanes voting for the same cell elect a leader that adds their number
+        const int cell = valid ? row * S + col : -1 - lane;
+        const unsigned same = __match_any_sync(0xffffffffu, cell);
+        if (valid && lane == __ffs(same) - 1) atomicAdd(hist + plane + cell, (unsigned)__popc(same));
+    };
+    const int total = ni * kTile;
+    for (int idx0 = 0; idx0 < total; idx0 += blockDim.x) {         // warp-uniform trip count (match_any needs full warps)
+        const int idx = idx0 + threadIdx.x;
+        const int i = idx / kTile, j = idx % kTile;
+        const bool pair = idx < total && j < nj && i0 + i < j0 + j;   // i < j only
+        int row = 0, col = 0;
+        bool done = false;
+        if (pair) {
+            done = fast_ok && fast_cell(fA[0][i], fA[1][i], fA[2][i], fB[0][j], fB[1][j], fB[2][j], s_over_pi, half_s, S, row, col);
+            if (!done) {
+                const int q = atomicAdd(&s_nq, 1);
+                if (q < kQueueCap) s_queue[q] = (unsigned short)((i << 8) | j);
+                else {
+                    // queue full (a tile of near-degenerate pairs): decide in place
+                    done = intersection_cell(sA[0][i], sA[1][i], sA[2][i], sB[0][j], sB[1][j], sB[2][j], half_over_s, s, S, row, col);
+                }
+            }
+        }
+        vote(pair && done, row, col, i, j);
+    }
+    __syncthreads();
+    const int nq = min(s_nq, kQueueCap);
+    if (stats && threadIdx.x == 0) { atomicAdd(stats + 0, (unsigned long long)nq); atomicAdd(stats + 1, 1ull); }
+    for (int q0 = 0; q0 < nq; q0 += blockDim.x) {
+        const int q = q0 + threadIdx.x;
+        int row = 0, col = 0, i = 0, j = 0;
+        bool ok = false;
+        if (q < nq) {
+            const int e = s_queue[q];
+            i = e >> 8; j = e & 255;
+            ok = intersection_cell(sA[0][i], sA[1][i], sA[2][i], sB[0][j], sB[1][j], sB[2][j], half_over_s, s, S, row, col);
+        }
+        vote(ok, row, col, i, j);
     }
 }
 
@@ -344,25 +459,16 @@ int sphere_map_dev(vpk_ctx* ctx, const double* d_lines, const int32_t* d_offsets
         if (weighted) VPK_CUDA(cudaMemsetAsync(d_whist, 0, sizeof(unsigned long long) * plane * B, ctx->stream));
         else VPK_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * plane * B, ctx->stream));
         if (items > 0) {
-            const int turn = ctx->work_turn;
-            ctx->work_turn ^= 1;
-            if (!ctx->ev_work[turn]) VPK_CUDA(cudaEventCreateWithFlags(&ctx->ev_work[turn], cudaEventDisableTiming));
-            else VPK_CUDA(cudaEventSynchronize(ctx->ev_work[turn]));      // the copy out of this buffer two calls ago
-            VPK_TRY(ctx->h_work[turn].ensure(items * sizeof(int4)));
             VPK_TRY(ctx->d_work.ensure(items * sizeof(int4)));
-            int4* w = ctx->h_work[turn].as<int4>();
-            int64_t k = 0;
-            for (int b = 0; b < B; ++b) {
-                int T = (h_offsets[b + 1] - h_offsets[b] + kTile - 1) / kTile;
-                for (int ti = 0; ti < T; ++ti)
-                    for (int tj = ti; tj < T; ++tj) w[k++] = make_int4(b, ti, tj, 0);
+            {
+                KernelScope ks(ctx, "sphere_items");
+                sphere_items_kernel<<<1, 1024, 0, ctx->stream>>>(d_offsets, B, ctx->d_work.as<int4>());
+                VPK_TRY(check_launch("sphere_items"));
             }
-            VPK_CUDA(cudaMemcpyAsync(ctx->d_work.p, w, items * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
-            VPK_CUDA(cudaEventRecord(ctx->ev_work[turn], ctx->stream));
             {
                 KernelScope ks(ctx, "sphere_votes");
                 sphere_votes_kernel<<<(unsigned)items, kVoteThreads, 0, ctx->stream>>>(
-                    d_lines, d_offsets, ctx->d_work.as<int4>(), S, d_weights, d_hist, d_whist);
+                    d_lines, d_offsets, ctx->d_work.as<int4>(), S, d_weights, d_hist, d_whist, nullptr);
                 VPK_TRY(check_launch("sphere_votes"));
             }
         }

@@ -103,11 +103,6 @@ struct vpk_ctx {
     // generic workspaces (stage-private buffers live in the stage states)
     vpk::DBuf d_lines, d_segments, d_offsets, d_work, d_hist, d_img, d_weights, d_misc;
     vpk::HBuf h_stage;
-    // pinned staging of the sphere-vote work list: two buffers used in turn, each guarded by an event
-    // recorded after its H2D copy, so that a call never waits for the stream
-    vpk::HBuf h_work[2];
-    cudaEvent_t ev_work[2] = {nullptr, nullptr};
-    int work_turn = 0;
 
     vpk::CnnState* cnn = nullptr;
     vpk::EmState* em = nullptr;

@@ -173,35 +173,95 @@ def gather_results(local_results, idx, n_images, world_size, dist=None):
 
 
 RAW_PER_IMAGE = ("status", "n_vp", "iterations", "vp", "sigma", "counts", "counts_weighted")
+_RAW_DTYPES = {"status": np.int32, "n_vp": np.int32, "iterations": np.int32, "vp": np.float64, "sigma": np.float64,
+               "counts": np.int32, "counts_weighted": np.float64}
+_RAW_TAIL = {"status": (), "n_vp": (), "iterations": (), "vp": (_lib.VPK_MAX_VP, 3), "sigma": (_lib.VPK_MAX_VP,),
+             "counts": (_lib.VPK_MAX_VP,), "counts_weighted": (_lib.VPK_MAX_VP,)}
+_gather_cache = {}
 
 
-def gather_raw(arrs, idx, offsets, n_images, world_size, dist=None):
-    """gather_results for the flat result arrays (`raw=True`): every rank contributes the arrays of its
-    shard (images `idx`, local `offsets`); rank 0 returns them reassembled in the batch's image order
-    (plus "offsets", the batch's (n_images + 1) prefix sums, for vp_assoc), the other ranks None."""
-    payload = {k: arrs[k] for k in RAW_PER_IMAGE}
-    payload["vp_assoc"] = arrs["vp_assoc"][:int(offsets[-1])]
-    payload["idx"] = np.asarray(idx, dtype=np.int64)
-    payload["n"] = np.diff(np.asarray(offsets, dtype=np.int64))
+def _blob_layout(n_img, n_seg):
+    """Byte offsets of the flat result arrays of a shard inside its gather blob (8-byte aligned fields)."""
+    lay, pos = {}, 0
+    for k in RAW_PER_IMAGE:
+        nb = n_img * int(np.prod(_RAW_TAIL[k], dtype=np.int64)) * np.dtype(_RAW_DTYPES[k]).itemsize
+        lay[k] = (pos, nb)
+        pos += (nb + 7) // 8 * 8
+    lay["vp_assoc"] = (pos, n_seg * 4)
+    pos += (n_seg * 4 + 7) // 8 * 8
+    return lay, pos
+
+
+def gather_raw(arrs, offsets_all, world_size, rank, dist=None):
+    """The path's only inter-rank exchange, for the flat result arrays (`raw=True`) of the shards
+    `shard_batch(offsets_all, world_size, r)`: ONE fixed-size `torch.distributed.gather` of a byte blob per rank
+    (every rank can compute every shard's sizes from the batch offsets, so nothing else is exchanged; NCCL moves
+    the blobs over NVLink, gloo over sockets in the CPU tests).  Rank 0 returns the arrays reassembled in the
+    batch's image order plus "offsets" (the batch's prefix sums, for vp_assoc); the other ranks return None."""
+    import torch
+    offsets_all = np.asarray(offsets_all, dtype=np.int64)
+    n_all = np.diff(offsets_all)
+    n_images = n_all.shape[0]
+    shards = [shard_batch(offsets_all, world_size, r) for r in range(world_size)]
+    sizes = [(len(ix), int(n_all[ix].sum())) for ix in shards]
+    layouts = [_blob_layout(*sz) for sz in sizes]
+    nbytes = max(l[1] for l in layouts)
+    use_cuda = dist is not None and world_size > 1 and dist.get_backend() == "nccl"
+    key = (nbytes, world_size, rank, use_cuda)
+    buf = _gather_cache.get(key)
+    if buf is None:
+        _gather_cache.clear()
+        host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=use_cuda)
+        buf = {"host": host}
+        if use_cuda:
+            buf["dev"] = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                buf["dev_all"] = torch.empty(world_size * nbytes, dtype=torch.uint8, device="cuda")
+                buf["host_all"] = torch.empty(world_size * nbytes, dtype=torch.uint8, pin_memory=True)
+        elif rank == 0:
+            buf["host_all"] = torch.empty(world_size * nbytes, dtype=torch.uint8)
+        _gather_cache[key] = buf
+    # pack this rank's arrays
+    lay, _ = layouts[rank]
+    hv = buf["host"].numpy()
+    n_img, n_seg = sizes[rank]
+    for k in RAW_PER_IMAGE:
+        pos, nb = lay[k]
+        hv[pos:pos + nb] = np.ascontiguousarray(arrs[k][:n_img], dtype=_RAW_DTYPES[k]).view(np.uint8).reshape(-1)
+    pos, nb = lay["vp_assoc"]
+    hv[pos:pos + nb] = np.ascontiguousarray(arrs["vp_assoc"][:n_seg], dtype=np.int32).view(np.uint8)
     if dist is None or world_size == 1:
-        parts = [payload]
-    else:
-        parts = [None] * world_size if dist.get_rank() == 0 else None
-        dist.gather_object(payload, parts, dst=0)
-        if dist.get_rank() != 0:
+        allv = hv[None, :]
+    elif use_cuda:
+        buf["dev"].copy_(buf["host"], non_blocking=True)
+        parts = list(buf["dev_all"].view(world_size, nbytes).unbind(0)) if rank == 0 else None
+        dist.gather(buf["dev"], parts, dst=0)
+        if rank != 0:
             return None
-    n = np.zeros(n_images, dtype=np.int64)
-    for p in parts:
-        n[p["idx"]] = p["n"]
-    off = np.zeros(n_images + 1, dtype=np.int64)
-    off[1:] = np.cumsum(n)
-    out = {k: np.empty((n_images,) + parts[0][k].shape[1:], dtype=parts[0][k].dtype) for k in RAW_PER_IMAGE}
-    out["vp_assoc"] = np.empty(int(off[-1]), dtype=np.int32)
-    out["offsets"] = off
-    for p in parts:
+        buf["host_all"].copy_(buf["dev_all"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        allv = buf["host_all"].numpy().reshape(world_size, nbytes)
+    else:
+        parts = list(buf["host_all"].view(world_size, nbytes).unbind(0)) if rank == 0 else None
+        dist.gather(buf["host"], parts, dst=0)
+        if rank != 0:
+            return None
+        allv = buf["host_all"].numpy().reshape(world_size, nbytes)
+    # reassemble in image order (vectorised: no per-image Python work)
+    out = {k: np.empty((n_images,) + _RAW_TAIL[k], dtype=_RAW_DTYPES[k]) for k in RAW_PER_IMAGE}
+    out["vp_assoc"] = np.empty(int(offsets_all[-1]), dtype=np.int32)
+    out["offsets"] = offsets_all
+    for r in range(world_size):
+        lay, _ = layouts[r]
+        ix = shards[r]
+        n_img, n_seg = sizes[r]
         for k in RAW_PER_IMAGE:
-            out[k][p["idx"]] = p[k]
-        lo = np.concatenate([[0], np.cumsum(p["n"])])
-        for j, i in enumerate(p["idx"]):
-            out["vp_assoc"][off[i]:off[i + 1]] = p["vp_assoc"][lo[j]:lo[j + 1]]
+            pos, nb = lay[k]
+            out[k][ix] = allv[r, pos:pos + nb].view(_RAW_DTYPES[k]).reshape((n_img,) + _RAW_TAIL[k])
+        pos, nb = lay["vp_assoc"]
+        part = allv[r, pos:pos + nb].view(np.int32)
+        n_r = n_all[ix]
+        local_start = np.concatenate([[0], np.cumsum(n_r)])[:-1]
+        dest = np.repeat(offsets_all[ix] - local_start, n_r) + np.arange(n_seg)
+        out["vp_assoc"][dest] = part
     return out
