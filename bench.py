@@ -15,10 +15,14 @@ EM -> VPs) over one synthetic batch of BASELINE.json config C.
         (every rank runs its own copy of the batch); `--strong` with N = 1 gives the one-GPU figure
         of the same workload.
 
-value    : whole-job images/s with the batch already resident in HBM (device
-           time from CUDA events on the launching stream, max over ranks).
-e2e      : same metric through the public API from pinned HOST buffers, H2D and
-           D2H inside the timed region.
+value    : whole-job images/s over K steps with the batch already resident in HBM, `--inflight` (default 3)
+           steps in flight per GPU -- one library context and host thread each (pipeline.StreamedPipeline):
+           the EM of a batch is a chain of dependent supersteps that leaves SMs idle, the next batches'
+           sphere mapping / CNN / pair pass fill them.  Device time between CUDA events on the library's
+           streams (first start mark -> last end mark), max over ranks.  `serial` is the same with ONE batch at a
+           time (the latency of a batch).
+e2e      : same metric through the public API from pinned HOST buffers, H2D and D2H (and, with several ranks,
+           the result gather) inside the timed region, the same number of calls in flight.
 roofline : dominant kernel of the step vs the measured peak in MEASURED_PEAKS.json.
 cpu_baseline / --impl reference : the CPU oracle (numpy/torch restatement of the
            reference path, oracle/) on a bounded sample of the same batch.
@@ -275,7 +279,11 @@ def run_ours(args, rank, world, local_rank):
         seg, off = seg_all, off_all
     B = len(off) - 1
     ws, bs = vcnn.random_weights(0, scale=args.weight_scale)
-    pipe = pipeline.Pipeline(local_rank, ws, bs, sphere_mode=args.sphere_mode)
+    # `depth` batches in flight: one library context + one host thread each (pipeline.StreamedPipeline); the serial
+    # and the profiled legs use the first context alone
+    depth = max(1, args.inflight)
+    sp = pipeline.StreamedPipeline(local_rank, ws, bs, depth=depth, sphere_mode=args.sphere_mode)
+    pipe = sp.pipes[0]
     ctx = pipe.ctx
 
     # pinned host inputs for the end-to-end leg
@@ -285,7 +293,8 @@ def run_ours(args, rank, world, local_rank):
 
     def barrier():
         torch.cuda.synchronize()
-        ctx.synchronize()
+        for q in sp.pipes:
+            q.ctx.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
@@ -307,12 +316,9 @@ def run_ours(args, rank, world, local_rank):
         best = min(best, t)
         streak = streak + 1 if t <= 1.05 * best else 0
         settle += 1
-    sampler = ClockSampler(local_rank, args.clock_period)
-    sampler.start()
+    # ---- serial leg: ONE batch at a time on one context (the latency of a batch; per-stage device times)
     barrier()
-    launches0 = ctx.launch_count()
     dev_ms, stage, step_ms = 0.0, {"sphere": 0.0, "cnn": 0.0, "em": 0.0}, []
-    t0 = time.perf_counter()
     for _ in range(args.steps):
         flush_l2()
         pipe.run()
@@ -322,11 +328,43 @@ def run_ours(args, rank, world, local_rank):
         for k in stage:
             stage[k] += ms[k]
     barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    launches = ctx.launch_count() - launches0
-    clocks = sampler.summary()
+    serial_ms = dev_ms / args.steps
     results = pipe.fetch(raw=True)
     n_ok = int(np.sum(results["status"] == 0))
+
+    # ---- resident leg -> `value`: K steps, `depth` of them in flight (step i runs on context i % depth); device time
+    # from the first context's start mark to the last context's end mark.  No global synchronisation (hence no L2
+    # flush) inside the region: every step streams > 1 GB of intermediates (similarity matrices, activations)
+    # through the 126 MB L2, nothing of a previous step survives in it.
+    import threading
+    for q in sp.pipes[1:]:
+        q.upload(seg_pin.numpy(), off_pin.numpy())
+        for _ in range(args.warmup):
+            q.run()
+    gate = threading.Barrier(depth)
+
+    def resident_worker(q):
+        k = sp.pipes.index(q)
+        gate.wait()
+        q.ctx.mark(0)
+        for _ in range(k, args.steps, depth):
+            q.run()
+        q.ctx.mark(1)
+        return True
+
+    sp.each(resident_worker)                      # one untimed pass in the overlapped regime
+    sampler = ClockSampler(local_rank, args.clock_period)
+    sampler.start()
+    barrier()
+    launches0 = sum(q.ctx.launch_count() for q in sp.pipes)
+    t0 = time.perf_counter()
+    sp.each(resident_worker)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    used = [q for k, q in enumerate(sp.pipes) if k < args.steps]
+    dev_total_ms = max(a.ctx.elapsed_ms(0, b.ctx, 1) for a in used for b in used)
+    launches = sum(q.ctx.launch_count() for q in sp.pipes) - launches0
+    clocks = sampler.summary()
 
     # ---- profiled leg: the same steps again with CUDA events around every kernel launch (on the
     # library's stream) -> per-kernel times, the dominant kernel and its roofline
@@ -343,20 +381,28 @@ def run_ours(args, rank, world, local_rank):
     prof = ctx.profile_read()
     em_stats = ctx.em_stats()
 
-    # ---- end-to-end leg from pinned host buffers: `e2e`
-    for _ in range(max(1, args.warmup // 2)):
-        pipe(seg_pin.numpy(), off_pin.numpy(), raw=True)
+    # ---- end-to-end leg from pinned host buffers -> `e2e`: every step is one public-API call (H2D, path, D2H), `depth`
+    # calls in flight; with several ranks the results of every step are then gathered on rank 0 (in step order, on this
+    # thread).  Wall clock between two barriers: host work, copies and the gather are all inside.
+    def e2e_steps(n_steps, seg_h, off_h, gather):
+        gms, last, full_ = 0.0, None, None
+        futs = [sp.submit(seg_h, off_h, raw=True) for _ in range(min(depth, n_steps))]
+        for i in range(n_steps):
+            last = futs[i % depth].result()
+            if i + depth < n_steps:
+                futs[i % depth] = sp.submit(seg_h, off_h, raw=True)
+            if gather:
+                # the path's only exchange: the per-image results of every shard end up on rank 0
+                tg = time.perf_counter()
+                full_ = pipeline.gather_raw(last, off_all, world, rank, dist)
+                gms += (time.perf_counter() - tg) * 1e3
+        return last, full_, gms
+
+    do_gather = args.strong and world > 1
+    e2e_steps(max(depth, args.warmup // 2), seg_pin.numpy(), off_pin.numpy(), do_gather)
     barrier()
     t0 = time.perf_counter()
-    gather_ms = 0.0
-    for _ in range(args.steps):
-        flush_l2()
-        out = pipe(seg_pin.numpy(), off_pin.numpy(), raw=True)
-        if args.strong and world > 1:
-            # the path's only exchange: the per-image results of every shard end up on rank 0
-            tg = time.perf_counter()
-            full = pipeline.gather_raw(out, off_all, world, rank, dist)
-            gather_ms += (time.perf_counter() - tg) * 1e3
+    out, full, gather_ms = e2e_steps(args.steps, seg_pin.numpy(), off_pin.numpy(), do_gather)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     h2d = seg.nbytes + off.nbytes
@@ -371,27 +417,22 @@ def run_ours(args, rank, world, local_rank):
     if args.strong and world > 1:
         if rank == 0:
             sa, oa = torch.from_numpy(seg_all).pin_memory(), torch.from_numpy(off_all).pin_memory()
-            for _ in range(2):
-                pipe(sa.numpy(), oa.numpy(), raw=True)
-            ctx.synchronize()
-            k1 = max(1, min(args.steps, 3))
+            e2e_steps(depth, sa.numpy(), oa.numpy(), False)
+            k1 = max(depth, min(args.steps, 4))
             t1 = time.perf_counter()
-            for _ in range(k1):
-                flush_l2()
-                pipe(sa.numpy(), oa.numpy(), raw=True)
-            ctx.synchronize()
+            e2e_steps(k1, sa.numpy(), oa.numpy(), False)
             one_gpu = {"e2e_images_per_s": B_all * k1 / (time.perf_counter() - t1), "steps": k1}
         barrier()
 
     # ---- reduce over ranks: max time, total images
-    t = torch.tensor([dev_ms / args.steps, e2e_ms, wall_ms / args.steps], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_total_ms / args.steps, e2e_ms, wall_ms / args.steps, serial_ms], dtype=torch.float64, device="cuda")
     tmin = t.clone()
     nimg = torch.tensor([float(B), float(n_ok)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
         dist.all_reduce(nimg, op=dist.ReduceOp.SUM)
-    ms_step, e2e_step, wall_step = [float(x) for x in t.tolist()]
+    ms_step, e2e_step, wall_step, serial_step = [float(x) for x in t.tolist()]
     total_images = int(nimg[0].item())
     n_ok = int(nimg[1].item())
     if args.strong:
@@ -502,7 +543,9 @@ def run_ours(args, rank, world, local_rank):
                        "segments_per_image_mean": float(np.mean(np.diff(off_all))),
                        "sphere_size": 500, "sphere_mode": args.sphere_mode, "cnn_weights": "random-init "
                        "(train_val.prototxt fillers x%g, seed 0)" % args.weight_scale,
-                       "l2": "flushed between steps (256 MiB memset)",
+                       "batches_in_flight": depth,
+                       "l2": "each step streams > 1 GB of intermediates through the 126 MB L2 (inputs larger than L2); the "
+                             "serial and profiled legs also flush it between steps (256 MiB memset)",
                        "parallelism": ("ONE batch sharded over the ranks (pipeline.shard_batch: LPT on N^2 + const), no data-path "
                                        "collective, results gathered on rank 0 inside the e2e region" if args.strong else
                                        "images sharded, no collective; every rank runs the same batch (fixed per-GPU work)")},
@@ -514,6 +557,9 @@ def run_ours(args, rank, world, local_rank):
                 "rank_time_ms": {"resident_max": ms_step, "resident_min": float(tmin[0].item()),
                                  "e2e_max": e2e_step, "e2e_min": float(tmin[1].item())},
                 "gather_ms_per_step_rank0": gather_ms / args.steps, "images_with_vps_after_gather": n_ok_all},
+            "serial": {"value": total_images / (serial_step * 1e-3), "unit": UNIT, "ms_per_step": serial_step,
+                       "what": "one batch at a time on one context, L2 flushed between steps (the latency of a batch; "
+                               "`stages_ms_per_step` and `step_ms` are of this leg)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
@@ -547,6 +593,7 @@ def main():
     ap.add_argument("--strong", action="store_true", help="shard ONE batch over the ranks (default for --gpus > 1)")
     ap.add_argument("--weak", action="store_true", help="every rank runs its own copy of the batch")
     ap.add_argument("--no-reference-em", action="store_true", help="skip the reference's own EM in the CPU baseline")
+    ap.add_argument("--inflight", type=int, default=3, help="batches in flight per GPU (library contexts + host threads)")
     ap.add_argument("--images", type=int, default=None, help="override the number of images per GPU")
     ap.add_argument("--sphere-mode", default="votes", choices=["votes", "curves"])
     ap.add_argument("--weight-scale", type=float, default=1.0,

@@ -58,6 +58,12 @@ VPK_API int vpk_synchronize(vpk_ctx* ctx);
 /* number of kernels this context has launched so far */
 VPK_API int64_t vpk_launch_count(const vpk_ctx* ctx);
 
+/* Device timestamps: vpk_mark records mark `slot` (0..3) on the context's stream; vpk_mark_elapsed returns the device
+ * time from one recorded mark to another, which may belong to another context of the same device (several contexts,
+ * each driven by its own host thread, keep several batches in flight; see pipeline.StreamedPipeline). */
+VPK_API int vpk_mark(vpk_ctx* ctx, int32_t slot);
+VPK_API int vpk_mark_elapsed(vpk_ctx* from, int32_t slot_from, vpk_ctx* to, int32_t slot_to, float* ms);
+
 /* per-kernel device timing (CUDA events on the context's stream). */
 VPK_API int vpk_profile_enable(vpk_ctx* ctx, int enable);
 VPK_API int vpk_profile_reset(vpk_ctx* ctx);

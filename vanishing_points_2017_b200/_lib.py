@@ -17,7 +17,7 @@ EM_OK, EM_NO_INITIAL_VPS, EM_NO_VPS_LEFT, EM_CAPACITY = 0, 1, 2, 3
 
 # every symbol include/vpk.h declares (tests check the .so exports each one)
 SYMBOLS = [
-    "vpk_create", "vpk_destroy", "vpk_abi_version", "vpk_last_error", "vpk_synchronize", "vpk_launch_count",
+    "vpk_create", "vpk_destroy", "vpk_abi_version", "vpk_last_error", "vpk_synchronize", "vpk_launch_count", "vpk_mark", "vpk_mark_elapsed",
     "vpk_profile_enable", "vpk_profile_reset", "vpk_profile_read", "vpk_lines_from_segments", "vpk_sphere_map",
     "vpk_cnn_load", "vpk_cnn_forward", "vpk_debug_gemm", "vpk_em_default_config", "vpk_em", "vpk_em_stats", "vpk_em_phase_cycles", "vpk_pipeline_upload", "vpk_pipeline_run",
     "vpk_pipeline_fetch", "vpk_pipeline_host", "vpk_pipeline_stage_ms", "vpk_horizon", "vpk_pipeline_horizon",
@@ -65,6 +65,8 @@ def load():
         lib.vpk_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         lib.vpk_destroy.argtypes = [C.c_void_p]
         lib.vpk_synchronize.argtypes = [C.c_void_p]
+        lib.vpk_mark.argtypes = [C.c_void_p, C.c_int32]
+        lib.vpk_mark_elapsed.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
         lib.vpk_profile_enable.argtypes = [C.c_void_p, C.c_int]
         lib.vpk_profile_reset.argtypes = [C.c_void_p]
         lib.vpk_profile_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -135,6 +137,16 @@ class Context:
 
     def synchronize(self):
         check(self.lib.vpk_synchronize(self.h), "vpk_synchronize")
+
+    def mark(self, slot=0):
+        """Device timestamp `slot` on this context's stream."""
+        check(self.lib.vpk_mark(self.h, int(slot)), "vpk_mark")
+
+    def elapsed_ms(self, slot_from, other, slot_to):
+        """Device time from this context's mark `slot_from` to `other`'s mark `slot_to` (same device)."""
+        ms = C.c_float()
+        check(self.lib.vpk_mark_elapsed(self.h, int(slot_from), other.h, int(slot_to), C.byref(ms)), "vpk_mark_elapsed")
+        return float(ms.value)
 
     def launch_count(self):
         return int(self.lib.vpk_launch_count(self.h))

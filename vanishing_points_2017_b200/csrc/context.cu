@@ -80,6 +80,7 @@ int vpk_destroy(vpk_ctx* ctx) {
     ctx->d_lines.release(); ctx->d_segments.release(); ctx->d_offsets.release(); ctx->d_work.release();
     ctx->d_hist.release(); ctx->d_img.release(); ctx->d_weights.release(); ctx->d_misc.release();
     ctx->h_stage.release();
+    for (auto& e : ctx->marks) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return VPK_OK;
@@ -93,6 +94,27 @@ int vpk_synchronize(vpk_ctx* ctx) {
 }
 
 int64_t vpk_launch_count(const vpk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int vpk_mark(vpk_ctx* ctx, int32_t slot) {
+    if (!ctx || slot < 0 || slot >= 4) { set_error("vpk_mark: bad argument"); return VPK_ERR_ARG; }
+    VPK_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->marks[slot]) VPK_CUDA(cudaEventCreate(&ctx->marks[slot]));
+    VPK_CUDA(cudaEventRecord(ctx->marks[slot], ctx->stream));
+    return VPK_OK;
+}
+
+int vpk_mark_elapsed(vpk_ctx* from, int32_t slot_from, vpk_ctx* to, int32_t slot_to, float* ms) {
+    if (!from || !to || !ms || slot_from < 0 || slot_from >= 4 || slot_to < 0 || slot_to >= 4 || !from->marks[slot_from] ||
+        !to->marks[slot_to] || from->device != to->device) {
+        set_error("vpk_mark_elapsed: bad argument (both marks must have been recorded, on the same device)");
+        return VPK_ERR_ARG;
+    }
+    VPK_CUDA(cudaSetDevice(from->device));
+    VPK_CUDA(cudaEventSynchronize(from->marks[slot_from]));
+    VPK_CUDA(cudaEventSynchronize(to->marks[slot_to]));
+    VPK_CUDA(cudaEventElapsedTime(ms, from->marks[slot_from], to->marks[slot_to]));
+    return VPK_OK;
+}
 
 int vpk_profile_enable(vpk_ctx* ctx, int enable) {
     if (!ctx) { set_error("null ctx"); return VPK_ERR_ARG; }

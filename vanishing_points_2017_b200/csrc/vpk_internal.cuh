@@ -104,6 +104,8 @@ struct vpk_ctx {
     vpk::DBuf d_lines, d_segments, d_offsets, d_work, d_hist, d_img, d_weights, d_misc;
     vpk::HBuf h_stage;
 
+    cudaEvent_t marks[4] = {nullptr, nullptr, nullptr, nullptr};   // vpk_mark: device timestamps on this context's stream
+
     vpk::CnnState* cnn = nullptr;
     vpk::EmState* em = nullptr;
     vpk::PipeState* pipe = nullptr;
