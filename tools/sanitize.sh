@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 CS=/usr/local/cuda/bin/compute-sanitizer
 run() {   # name, tool, extra env, command...
     local name=$1 tool=$2; shift 2
-    timeout 900 $CS --tool $tool --print-limit 20 --error-exitcode 9 "$@" > gpurun_out/${TAG}_sanitize_${name}_${tool}.log 2>&1
+    timeout 420 $CS --tool $tool --print-limit 20 --error-exitcode 9 "$@" > gpurun_out/${TAG}_sanitize_${name}_${tool}.log 2>&1
     local rc=$?
     { echo "== $name / $tool: exit $rc"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard|Invalid|images with VPs|passed|failed" gpurun_out/${TAG}_sanitize_${name}_${tool}.log | sort | uniq -c | head -20; } \
         >> gpurun_out/${TAG}_sanitize_summary.txt
