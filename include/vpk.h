@@ -156,6 +156,15 @@ VPK_API int vpk_em(vpk_ctx* ctx, const double* lines, const double* segments, co
            const double* init_vp, const int32_t* init_vp_offsets,
            const vpk_em_config* cfg, vpk_em_result* out);
 
+/* 'distribution' of the reference's result dict (vp_localisation.py:441-442): the PDF namedtuple of
+ * probability_functions.py:5 that calc_probabilities (:99-120) returns for the LAST E-step, for image `image` of the
+ * last vpk_em / vpk_pipeline_run call of this context.  Evaluated on the device from the planes that superstep left
+ * in the EM workspace, so it must be asked for before the next EM call and only for batches that ran in one
+ * workspace wave.  n_vp / n_lines: the image's 'vp' rows and lines (checked).  Caller-allocated float64 arrays:
+ * p_v (n_vp), p_lv (n_lines, n_vp), p_vl (n_vp, n_lines), p_l (n_lines), lvsq (n_lines, n_vp), angles (n_vp, 2). */
+VPK_API int vpk_em_distribution(vpk_ctx* ctx, int32_t image, int32_t n_vp, int32_t n_lines, double* p_v, double* p_lv,
+                                double* p_vl, double* p_l, double* lvsq, double* angles);
+
 /* Profiling runs only (vpk_profile_enable): accumulated algorithmic work of the weight-matrix
  * products (vp_localisation.py:515-524) since the last reset: out[0] = bytes of similarity
  * matrix consumed (8 N^2 per product), out[1] = flops (2 M N^2 per product), out[2] = number

@@ -155,3 +155,23 @@ def test_loop_modes_are_bit_identical(em, monkeypatch, N):
         np.testing.assert_array_equal(res["vp"], ref["vp"], err_msg=str(key))
         np.testing.assert_array_equal(res["vp_assoc"], ref["vp_assoc"], err_msg=str(key))
         np.testing.assert_array_equal(res["decision_metric"], ref["decision_metric"], err_msg=str(key))
+
+
+def test_distribution_is_the_pdf_tuple_of_the_last_estep(em):
+    """result['distribution'] (vp_localisation.py:441-442; probability_functions.py:5, :99-120), evaluated on the
+    device from the planes of the last E-step."""
+    sc = synth.make_scene(9301, 420, 800, 600, noise_deg=1.0)
+    img = so.votes_to_image(so.sphere_votes(sc["lines"], 500))
+    resp = synth.ideal_response(sc["vps"], seed=3)
+    ref = vo.expectation_maximisation(sc["lines"].copy(), sc["segments"].copy(), resp.copy(), sphere_image=img)
+    res = em.expectation_maximisation(sc["lines"].copy(), sc["segments"].copy(), resp.copy(), sphere_image=img)
+    compare(res, ref["vp"], ref["counts"], ref["vp_assoc"], ref["sigma"], ref["iterations"])
+    p, q = res["distribution"], ref["distribution"]
+    assert type(p).__name__ == "PDF" and p._fields == ("v", "lv", "vl", "l", "lvsq", "angles")
+    M, N = ref["vp"].shape[0], 420
+    assert p.v.shape == (M,) and p.lv.shape == (N, M) and p.vl.shape == (M, N) and p.l.shape == (N,)
+    np.testing.assert_allclose(p.angles, q.angles, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(p.v, q.v, rtol=1e-4)
+    np.testing.assert_allclose(p.lvsq, q.lvsq, rtol=1e-3, atol=1e-12)          # VPs agree to 1e-4 rad, not bit for bit
+    np.testing.assert_allclose(p.vl.sum(axis=0)[q.l > 1e-12], 1.0, rtol=1e-9)   # responsibilities of unclamped lines
+    assert np.array_equal(np.argmax(p.vl, axis=0)[q.l > 1e-9], np.argmax(q.vl, axis=0)[q.l > 1e-9])

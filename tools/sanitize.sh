@@ -8,19 +8,22 @@ mkdir -p gpurun_out
 CS=/usr/local/cuda/bin/compute-sanitizer
 run() {   # name, tool, extra env, command...
     local name=$1 tool=$2; shift 2
-    timeout 420 $CS --tool $tool --print-limit 20 --error-exitcode 9 "$@" > gpurun_out/${TAG}_sanitize_${name}_${tool}.log 2>&1
+    timeout 420 $CS --tool $tool --print-limit 40 --error-exitcode 9 "$@" > gpurun_out/${TAG}_sanitize_${name}_${tool}.log 2>&1
     local rc=$?
     { echo "== $name / $tool: exit $rc"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard|Invalid|images with VPs|passed|failed" gpurun_out/${TAG}_sanitize_${name}_${tool}.log | sort | uniq -c | head -20; } \
         >> gpurun_out/${TAG}_sanitize_summary.txt
 }
 rm -f gpurun_out/${TAG}_sanitize_summary.txt
-# the whole path on a small YUD-shaped batch (device-driven EM loop)
+# memcheck: the default path (device-driven EM loop: CUDA graph of conditional WHILE nodes) and the large-image paths
 run pipe12 memcheck python tools/run_once.py --config 2 --images 12
-run pipe12 racecheck python tools/run_once.py --config 2 --images 12
-# host-driven loop (ordinary launches)
-VPK_EM_HOST_LOOP=1 run pipe12_hostloop racecheck python tools/run_once.py --config 2 --images 12
-# one large image: N = 1600 takes the paths above the slab-split threshold (1536)
 run em1600 memcheck python tools/run_em_once.py --n 1600
-run em1600 racecheck python tools/run_em_once.py --n 1600
-run em3200 racecheck python tools/run_em_once.py --n 3200 --num-iter 3
+# racecheck needs ordinary launches (it dies on graphs whose kernels set conditional handles): host-driven loop,
+# the same kernels; N = 1600 / 3200 take the 2- and 4-CTA cluster split of the weight-matrix kernel (DSMEM reduction)
+export NV_COMPUTE_SANITIZER_MAX_RACECHECK_HAZARDS=4096
+VPK_EM_HOST_LOOP=1 run pipe12_hostloop racecheck python tools/run_once.py --config 2 --images 12
+VPK_EM_HOST_LOOP=1 run em1600_hostloop racecheck python tools/run_em_once.py --n 1600
+VPK_EM_HOST_LOOP=1 run em3200_hostloop racecheck python tools/run_em_once.py --n 3200 --num-iter 3
+# the persistent cluster-per-image kernel (mbarrier ring carried across images, DSMEM mirror, work queue)
+VPK_EM_MODE=fused run pipe12_fused racecheck python tools/run_once.py --config 2 --images 12
+VPK_EM_MODE=fused run pipe12_fused memcheck python tools/run_once.py --config 2 --images 12
 cat gpurun_out/${TAG}_sanitize_summary.txt

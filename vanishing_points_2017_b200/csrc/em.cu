@@ -930,6 +930,48 @@ __global__ void __launch_bounds__(kFThreads) em_poste_kernel(EmParams P, TierCtl
 }
 
 // ---------------------------------------------------------------------------
+// 'distribution' of the reference's result dict (vp_localisation.py:441-442: the PDF namedtuple of
+// probability_functions.py:5, :99-120 for the last E-step) from the planes the last superstep left in the slot
+// workspace.  out (doubles): p_v (M) | angles (M,2) | p_l (N) | p_lv (N,M) | lvsq (N,M) | p_vl (M,N)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) em_distribution_kernel(const EmSlot* __restrict__ slot, const double* __restrict__ ws, double* __restrict__ out) {
+    const EmSlot& st = *slot;
+    const int N = st.N, M = st.M;
+    const Img im = make_img(N, const_cast<double*>(ws) + st.ws_off, nullptr);
+    double* p_v = out;
+    double* angles = p_v + M;
+    double* p_l = angles + 2 * (size_t)M;
+    double* p_lv = p_l + N;
+    double* lvsq = p_lv + (size_t)N * M;
+    double* p_vl = lvsq + (size_t)N * M;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < M) {
+        const int m = n;
+        p_v[m] = st.pv[m];
+        const double* v = st.nxt[m];                                  // the final E-step runs on v[i + 1] (:415)
+        const double beta = asin(v[1]);
+        double inner = v[0] / cos(beta);
+        const bool isn = isnan(inner);
+        inner = fmax(fmin(inner, 1.0), -1.0);
+        if (isn) inner = nan("");
+        angles[2 * m] = asin(inner);                                  // calc_angles (probability_functions.py:252-259)
+        angles[2 * m + 1] = beta;
+    }
+    if (n >= N) return;
+    double pl = 0.0, part[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int m = 0; m < M; ++m) {
+        const double lv = im.lvsq[(size_t)m * N + n];
+        const double plv = exp(-(lv * st.inv2s[m])) * st.coef[m];    // calc_plv (:140-145), as the E-step evaluates it
+        lvsq[(size_t)n * M + m] = lv;
+        p_lv[(size_t)n * M + m] = plv;
+        part[m & 7] += plv * st.pv[m];                                // the E-step's own summation order (estep_tile)
+        p_vl[(size_t)m * N + n] = im.pvl[(size_t)m * N + n];
+    }
+    for (int w = 0; w < 8; ++w) pl += part[w];
+    p_l[n] = pl < 1e-12 ? 1e-12 : pl;                                 // :117
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 // Device-driven loop: a CUDA graph of conditional WHILE nodes, one per tier of grid sizes
@@ -1452,6 +1494,47 @@ int vpk_em_stats(vpk_ctx* ctx, uint64_t out[6], int reset) {
     if (!ctx || !out) { set_error("vpk_em_stats: bad argument"); return VPK_ERR_ARG; }
     for (int k = 0; k < 6; ++k) out[k] = ctx->em ? ctx->em->totals[k] : 0;
     if (reset && ctx->em) for (auto& t : ctx->em->totals) t = 0;
+    return VPK_OK;
+}
+
+int vpk_em_distribution(vpk_ctx* ctx, int32_t image, int32_t n_vp, int32_t n_lines, double* p_v, double* p_lv, double* p_vl,
+                        double* p_l, double* lvsq, double* angles) {
+    if (!ctx || !ctx->em || image < 0 || !p_v || !p_lv || !p_vl || !p_l || !lvsq || !angles) { set_error("vpk_em_distribution: bad argument"); return VPK_ERR_ARG; }
+    EmState* st = ctx->em;
+    EmWave& W = st->wave;
+    if (W.begun || W.n <= 0 || W.begin != 0 || W.end != W.key_B) {
+        set_error("vpk_em_distribution: the planes of the last E-step are kept for batches that ran in one workspace wave only");
+        return VPK_ERR_STATE;
+    }
+    const SlotDesc* hd = st->h_desc.as<SlotDesc>();
+    int slot = -1;
+    for (int i = 0; i < W.n; ++i) if (hd[i].img == image) { slot = i; break; }
+    if (slot < 0) { set_error("vpk_em_distribution: image %d is not part of the last batch", image); return VPK_ERR_ARG; }
+    VPK_CUDA(cudaSetDevice(ctx->device));
+    EmSlot hs;
+    VPK_CUDA(cudaMemcpy(&hs, st->slots.as<EmSlot>() + slot, sizeof(EmSlot), cudaMemcpyDeviceToHost));
+    if (hs.status != VPK_EM_OK || hs.M != n_vp || hs.N != n_lines) {
+        set_error("vpk_em_distribution: image %d finished with status %d, %d hypotheses, %d lines (caller expects %d, %d)", image, hs.status,
+                  hs.M, hs.N, n_vp, n_lines);
+        return VPK_ERR_ARG;
+    }
+    const size_t M = (size_t)hs.M, N = (size_t)hs.N, total = 3 * M + N + 3 * N * M;
+    VPK_TRY(ctx->d_misc.ensure(total * sizeof(double)));
+    double* d = ctx->d_misc.as<double>();
+    {
+        KernelScope ks(ctx, "em_distribution");
+        const unsigned blocks = (unsigned)((std::max(N, M) + 255) / 256);
+        em_distribution_kernel<<<blocks, 256, 0, ctx->stream>>>(st->slots.as<EmSlot>() + slot, st->ws.as<double>(), d);
+        VPK_TRY(check_launch("em_distribution"));
+    }
+    auto D2H = [&](double* dst, const double* src, size_t n) { return cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream); };
+    VPK_CUDA(D2H(p_v, d, M));
+    VPK_CUDA(D2H(angles, d + M, 2 * M));
+    VPK_CUDA(D2H(p_l, d + 3 * M, N));
+    VPK_CUDA(D2H(p_lv, d + 3 * M + N, N * M));
+    VPK_CUDA(D2H(lvsq, d + 3 * M + N + N * M, N * M));
+    VPK_CUDA(D2H(p_vl, d + 3 * M + N + 2 * N * M, N * M));
+    VPK_CUDA(cudaStreamSynchronize(ctx->stream));
     return VPK_OK;
 }
 

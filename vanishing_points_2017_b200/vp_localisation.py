@@ -7,11 +7,27 @@ reference's skeleton dict of None (:205-206).  The whole EM (pair similarity,
 kNN line rating, E/M steps, split, merge, final refit) runs inside one
 persistent CUDA kernel behind libvpk.so's C ABI (`vpk_em`).
 """
+import collections
 import ctypes as C
 
 import numpy as np
 
 from . import _lib
+
+# the reference's probability_functions.PDF (probability_functions.py:5): type of result['distribution']
+PDF = collections.namedtuple("PDF", "v lv vl l lvsq angles")
+
+
+def em_distribution(image, n_vp, n_lines, ctx=None):
+    """result['distribution'] of image `image` of the LAST EM call on `ctx` (vp_localisation.py:441-442): evaluated on
+    the device from the planes of the last E-step (`vpk_em_distribution`); ask before the next EM call."""
+    ctx = ctx or _lib.default_context()
+    M, N = int(n_vp), int(n_lines)
+    a = {"v": np.empty(M), "lv": np.empty((N, M)), "vl": np.empty((M, N)), "l": np.empty(N), "lvsq": np.empty((N, M)),
+         "angles": np.empty((M, 2))}
+    _lib.check(ctx.lib.vpk_em_distribution(ctx.h, int(image), M, N, _lib.ptr(a["v"]), _lib.ptr(a["lv"]), _lib.ptr(a["vl"]),
+                                           _lib.ptr(a["l"]), _lib.ptr(a["lvsq"]), _lib.ptr(a["angles"])), "vpk_em_distribution")
+    return PDF(**a)
 
 _SKELETON = {"vp_assoc": None, "vp": None, "counts": None, "count_id": None, "decision_metric": None,
              "iterations": 0}
@@ -122,5 +138,5 @@ def expectation_maximisation(l, lp, cnn_response, num_iter=100, sphere_image=Non
     if res["vp"] is None:
         return {k: res[k] for k in _SKELETON}
     res.pop("status", None)
-    res["distribution"] = None       # the reference returns its PDF namedtuple here; not exported (lazy)
+    res["distribution"] = em_distribution(0, res["vp"].shape[0], N, ctx)       # the PDF tuple of the last E-step (:441-442)
     return res
