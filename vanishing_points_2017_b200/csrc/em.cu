@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(kWThreads, 2) em_wmat_kernel(EmParams P, int c
 // ---------------------------------------------------------------------------
 // em_post: one CTA per active slot
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPostThreads) em_post_kernel(EmParams P, TierCtl tc) {
+__global__ void __launch_bounds__(kPostThreads, 2) em_post_kernel(EmParams P, TierCtl tc) {
     __shared__ __align__(16) EmSlot st;
     __shared__ PostScratch sc;
     const int step = P.ctl[3], cur = step & 1;
@@ -1003,6 +1003,7 @@ struct EmWave {
     bool begun = false;                    // wave_begin done, wave_run pending
     bool device_loop = true;
     int mode = MODE_FUSED, cluster = 8, keep = 0;
+    int waves_run = 0;                     // waves of the current / last batch that have run (1: its planes are still in the workspace)
     int begin = 0, end = 0, n = 0, G = 0;
     size_t budget = 0;
     std::vector<int32_t> order;
@@ -1469,6 +1470,7 @@ int em_dev(vpk_ctx* ctx, const double* d_lines, const double* d_segments, const 
         VPK_TRY(st->ctl.ensure((kMaxGroups + 1) * kCtlInts * sizeof(int)));
         VPK_TRY(st->stats.ensure(32 * sizeof(unsigned long long)));
         W.begin = 0;
+        W.waves_run = 0;
         W.key_B = B; W.key_off = h_offsets;
         memcpy(&W.key_P, &P, sizeof(EmParams));
     }
@@ -1479,6 +1481,7 @@ int em_dev(vpk_ctx* ctx, const double* d_lines, const double* d_segments, const 
         }
         if (phase == EM_EARLY) return VPK_OK;
         VPK_TRY(wave_run(ctx, st));
+        ++W.waves_run;
         W.begin = W.end;
     }
     return VPK_OK;
@@ -1502,7 +1505,7 @@ int vpk_em_distribution(vpk_ctx* ctx, int32_t image, int32_t n_vp, int32_t n_lin
     if (!ctx || !ctx->em || image < 0 || !p_v || !p_lv || !p_vl || !p_l || !lvsq || !angles) { set_error("vpk_em_distribution: bad argument"); return VPK_ERR_ARG; }
     EmState* st = ctx->em;
     EmWave& W = st->wave;
-    if (W.begun || W.n <= 0 || W.begin != 0 || W.end != W.key_B) {
+    if (W.begun || W.n <= 0 || W.waves_run != 1 || W.n != W.key_B) {
         set_error("vpk_em_distribution: the planes of the last E-step are kept for batches that ran in one workspace wave only");
         return VPK_ERR_STATE;
     }
