@@ -69,3 +69,36 @@ def test_pipeline_is_deterministic_and_shard_invariant(pipe):
     for a, b in zip(full, got):
         if a["vp"] is not None:
             np.testing.assert_array_equal(a["vp"], b["vp"])
+
+
+def test_streamed_pipeline_keeps_batches_in_flight_and_equals_the_serial_results(pipe):
+    """pipeline.StreamedPipeline: several library contexts, each driven by its own host thread, keep several batches
+    in flight on one GPU.  Every batch still runs alone on its context, so the results are bit-identical to the
+    serial Pipeline's, in submission order."""
+    from vanishing_points_2017_b200 import pipeline
+    p, ws, bs = pipe
+    batches = []
+    for k in range(5):
+        b = synth.make_batch(2, n_images=6 + k)
+        batches.append((b["segments"], b["offsets"]))
+    serial = [p(seg, off, raw=True) for seg, off in batches]
+    sp = pipeline.StreamedPipeline(0, ws, bs, depth=2, sphere_mode="votes")
+    try:
+        assert sp.depth == 2 and sp.pipes[0].ctx.h != sp.pipes[1].ctx.h
+        streamed = list(sp.map(batches, raw=True))
+        futs = [sp.submit(seg, off, raw=True) for seg, off in batches[:2]]      # both contexts busy at once
+        streamed += [f.result() for f in futs]
+    finally:
+        sp.close()
+    for a, b in zip(serial + serial[:2], streamed):
+        for key in ("status", "n_vp", "iterations", "counts"):
+            np.testing.assert_array_equal(a[key], b[key])
+        nv = a["n_vp"]
+        for i in range(len(nv)):
+            np.testing.assert_array_equal(a["vp"][i, :nv[i]], b["vp"][i, :nv[i]])
+            np.testing.assert_array_equal(a["sigma"][i, :nv[i]], b["sigma"][i, :nv[i]])
+    # device marks across contexts
+    c0, c1 = pipeline._lib.Context(0), pipeline._lib.Context(0)
+    c0.mark(0); c1.mark(1)
+    assert c0.elapsed_ms(0, c1, 1) >= 0.0
+    c0.close(); c1.close()

@@ -836,6 +836,7 @@ __global__ void __launch_bounds__(kFThreads, 2) em_fused_kernel(EmParams P, int 
             mark(6);
         }
         if (P.stats && rank == 0 && tid == 0) atomicMax(P.stats + 5, (unsigned long long)steps);
+        if (rank == 0 && steps > 0) copy_slot(P.slots + slot, &S.st, T);      // the final state (vpk_em_distribution reads it)
     }
     if (P.stats && rank == 0 && tid == 0)
         for (int k = 0; k < 7; ++k) atomicAdd(P.stats + 8 + k, (unsigned long long)S.mark[k]);
