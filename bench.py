@@ -470,9 +470,9 @@ def run_ours(args, rank, world, local_rank):
                     byt = float(np.sum(8.0 * n * n + 32.0 * n))
                 elif kname == "sphere_votes":
                     byt = float(np.sum(24.0 * n) + 4.0 * 500 * 500 * B)
-                elif kname == "lrn_pool1":
+                elif kname in ("lrn_pool1", "pool1"):
                     byt = B * (96 * 123 * 123 * 2 + 96 * 61 * 61 * 2.0)
-                elif kname == "lrn_pool2":
+                elif kname in ("lrn_pool2", "pool2"):
                     byt = B * (256 * 61 * 61 * 2 + 256 * 30 * 30 * 2.0)
                 else:
                     byt = 0.0

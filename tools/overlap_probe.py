@@ -14,7 +14,7 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 name, seg, off = bench.make_workload(cfg, 0, None)
 B = len(off) - 1
 ws, bs = vcnn.random_weights(0)
-for depth in (1, 2, 3):
+for depth in [int(x) for x in os.environ.get("DEPTHS", "1,2,3").split(",")]:
     pipes = [pipeline.Pipeline(0, ws, bs, sphere_mode="votes", ctx=_lib.Context(0)) for _ in range(depth)]
     for p in pipes:
         p.upload(seg, off)

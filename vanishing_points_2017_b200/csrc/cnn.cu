@@ -247,7 +247,14 @@ int launch_gemm(vpk_ctx* ctx, const GemmCall& c) {
         set_error("%s: bad split-K configuration", c.name);
         return VPK_ERR_ARG;
     }
-    dim3 grid(m_tiles, n_tiles, c.groups * ksplit);
+    const int fold = c.p.fold > 1 ? c.p.fold : 1;
+    if (fold > 1 && (!c.p.lrn || ksplit > 1 || n_tiles != 1 || c.groups % fold || fold * c.p.bn > 256 || c.p.n_valid != c.p.bn ||
+                     c.p.c_col_group != c.p.bn)) {
+        set_error("%s: bad group-folding configuration", c.name);
+        return VPK_ERR_ARG;
+    }
+    if (c.p.lrn && (n_tiles != 1 || ksplit > 1 || c.p.out_f32)) { set_error("%s: the fused LRN needs all channels in one tile", c.name); return VPK_ERR_ARG; }
+    dim3 grid(m_tiles, n_tiles, (c.groups / fold) * ksplit);
     const size_t stage = kABytes + (size_t)c.p.bn * kBK * 2;
     KernelScope ks(ctx, c.name);
     if (c.p.bn <= 128) {
@@ -353,13 +360,14 @@ int cnn_forward_dev(vpk_ctx* ctx, const uint8_t* d_images, int32_t n, float* d_s
     c.p.m_total = n * 15625; c.p.k_blocks = 3; c.p.cblocks = 1; c.p.taps_x = 1; c.p.row_pitch = 125;
     c.p.hp_wp = 15625; c.p.wp = 125; c.p.h_valid = 123; c.p.w_valid = 123;
     c.p.out_hp_wp = 123 * 123; c.p.out_wp = 123; c.p.out_pad = 0; c.p.ldc = 96; c.p.n_valid = 96; c.p.relu = 1; c.p.bn = 96;
+    c.p.lrn = 1;                                           // norm1 (cnn/deploy.prototxt:34-44) in the epilogue: a thread owns a pixel's 96 channels
     c.p.bias = s->b[0].as<float>(); c.p.out = s->c1.p;
     VPK_TRY(launch_gemm(ctx, c));
     {
-        KernelScope ks(ctx, "lrn_pool1");
+        KernelScope ks(ctx, "pool1");                      // pool1 (:45-55): 3x3 / 2 ceil-mode maximum of the normalised map
         long long t = (long long)n * 31 * 31 * 12;
-        lrn_pool_kernel<true><<<(unsigned)((t + 255) / 256), 256, 0, ctx->stream>>>(s->c1.as<bf>(), n, 123, 123, 96, 61, 61, 2, 128, 48, 64, s->a2.as<bf>());
-        VPK_TRY(check_launch("lrn_pool1"));
+        lrn_pool_kernel<false><<<(unsigned)((t + 255) / 256), 256, 0, ctx->stream>>>(s->c1.as<bf>(), n, 123, 123, 96, 61, 61, 2, 128, 48, 64, s->a2.as<bf>());
+        VPK_TRY(check_launch("pool1"));
     }
     // conv2: 5x5 pad 2, 2 groups of 48 (stored as 64) -> 128 each
     memset(&c, 0, sizeof(c));
@@ -368,13 +376,15 @@ int cnn_forward_dev(vpk_ctx* ctx, const uint8_t* d_images, int32_t n, float* d_s
     c.p.m_total = n * 4225; c.p.k_blocks = 25; c.p.cblocks = 1; c.p.taps_x = 5; c.p.row_pitch = 65; c.p.a_col_group = 64; c.p.b_row_group = 128;
     c.p.hp_wp = 4225; c.p.wp = 65; c.p.h_valid = 61; c.p.w_valid = 61;
     c.p.out_hp_wp = 61 * 61; c.p.out_wp = 61; c.p.out_pad = 0; c.p.ldc = 256; c.p.c_col_group = 128; c.p.n_valid = 128; c.p.relu = 1; c.p.bn = 128;
+    c.p.lrn = 1; c.p.fold = 2;        // norm2 (cnn/deploy.prototxt:82-92) in the epilogue: one CTA computes both groups of its
+                                      // pixels, so the window of channels 126..129 crosses the group seam inside a thread
     c.p.bias = s->b[1].as<float>(); c.p.out = s->c2.p;
     VPK_TRY(launch_gemm(ctx, c));
     {
-        KernelScope ks(ctx, "lrn_pool2");
+        KernelScope ks(ctx, "pool2");     // pool2 (:93-103)
         long long t = (long long)n * 15 * 15 * 32;
-        lrn_pool_kernel<true><<<(unsigned)((t + 255) / 256), 256, 0, ctx->stream>>>(s->c2.as<bf>(), n, 61, 61, 256, 30, 30, 1, 256, 256, 256, s->a3.as<bf>());
-        VPK_TRY(check_launch("lrn_pool2"));
+        lrn_pool_kernel<false><<<(unsigned)((t + 255) / 256), 256, 0, ctx->stream>>>(s->c2.as<bf>(), n, 61, 61, 256, 30, 30, 1, 256, 256, 256, s->a3.as<bf>());
+        VPK_TRY(check_launch("pool2"));
     }
     // conv3: 3x3 pad 1, 256 -> 384, written into conv4's padded input
     memset(&c, 0, sizeof(c));

@@ -170,20 +170,24 @@ __global__ void __launch_bounds__(kPairThreads) em_pair_kernel(EmParams P) {
         if (tid < JB && jb + tid < N) s_seg[tid] = seg_pre(load_seg(im.lp, jb + tid));
         __syncthreads();
         const int jn = min(JB, N - jb);
-        for (int jj = g; jj < jn; jj += G) {
-            const int j = jb + jj;
-            double val = 0.0;
+        // two rows per trip: the arithmetic of both pairs first (independent chains for the FP64 pipe), then the
+        // candidate-list updates, stores and column sums in row order (the same order as one row per trip)
+        for (int jj = g; jj < jn; jj += 2 * G) {
+            const int ja = jb + jj, jc = ja + G;
+            const bool two = jj + G < jn;
+            double d2a = 16.0, vala = 0.0, d2c = 16.0, valc = 0.0;          // diagonal: ldist = 4 (:82), lsim = 0 (:105)
             if (live) {
-                if (j == k) knn_insert(s_kd + tid, s_kj + tid, kPairThreads, cnt, 16.0, j);   // diagonal: ldist = 4 (:82), lsim = 0 (:105)
-                else {
-                    const SegPre& sj = s_seg[jj];
-                    const double d2 = seg_distance2(sj, sk);
-                    val = similarity_pre(sj, sk, d2);
-                    knn_insert(s_kd + tid, s_kj + tid, kPairThreads, cnt, d2, j);
-                }
+                if (ja != k) { const SegPre& sj = s_seg[jj]; d2a = seg_distance2(sj, sk); vala = similarity_pre(sj, sk, d2a); }
+                if (two && jc != k) { const SegPre& sj = s_seg[jj + G]; d2c = seg_distance2(sj, sk); valc = similarity_pre(sj, sk, d2c); }
+                knn_insert(s_kd + tid, s_kj + tid, kPairThreads, cnt, d2a, ja);
             }
-            slab[(size_t)j * kTK + lsim_swz(j, col)] = val;
-            part += val;
+            slab[(size_t)ja * kTK + lsim_swz(ja, col)] = vala;
+            part += vala;
+            if (two) {
+                if (live) knn_insert(s_kd + tid, s_kj + tid, kPairThreads, cnt, d2c, jc);
+                slab[(size_t)jc * kTK + lsim_swz(jc, col)] = valc;
+                part += valc;
+            }
         }
     }
     s_cnt[tid] = cnt;

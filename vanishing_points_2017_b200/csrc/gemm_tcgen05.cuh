@@ -44,6 +44,11 @@ struct GemmParams {
     int c_col_group;                       // output column offset per group
     int n_valid;                           // output columns per group
     int relu, out_f32;
+    int lrn;                               // fused LRN (ACROSS_CHANNELS, size 5, alpha 1e-4, beta 0.75, k 1; cnn/deploy.prototxt:34-44)
+                                           // after bias + ReLU; needs all n_valid channels in ONE tile (n_valid <= bn, groups == 1)
+    int fold;                              // > 1: ONE CTA computes `fold` consecutive groups of its rows one after the other into
+                                           // adjacent TMEM column ranges (grid.z = groups / fold), so that the fused LRN sees the
+                                           // channels of all groups (conv2: 2 x 128; needs lrn, n_valid == bn, fold * bn <= 256)
     int bn;                                // N tile (multiple of 16, <= 256)
     const float* bias;                     // [groups * n_valid] or nullptr
     void* out;
@@ -141,11 +146,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int m0 = blockIdx.x * kBM;
     const int n0 = blockIdx.y * p.bn;
     const int nsplit = p.ksplit > 1 ? p.ksplit : 1;
-    const int g = blockIdx.z / nsplit, ksp = blockIdx.z - g * nsplit;
+    const int nfold = p.fold > 1 ? p.fold : 1;
+    const int g = (blockIdx.z / nsplit) * nfold, ksp = blockIdx.z - (blockIdx.z / nsplit) * nsplit;      // first group of this CTA
     const int kb_per = (p.k_blocks + nsplit - 1) / nsplit;
     const int kb0 = ksp * kb_per, nkb = min(kb_per, p.k_blocks - kb0);       // host guarantees nkb >= 1
     uint32_t ncols = 32;
-    while ((int)ncols < p.bn) ncols <<= 1;
+    while ((int)ncols < p.bn * nfold) ncols <<= 1;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -166,25 +172,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
-            for (int i = 0; i < nkb; ++i) {
+            for (int it = 0; it < nkb * nfold; ++it) {
+                const int gi = it / nkb, i = it - gi * nkb, ge = g + gi;
                 const int kb = kb0 + i;
-                const int s = i % kStages;
-                const uint32_t ph = (uint32_t)(i / kStages) & 1u;
+                const int s = it % kStages;
+                const uint32_t ph = (uint32_t)(it / kStages) & 1u;
                 mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
                 const uint32_t full = smem_u32(&bar_full[s]);
                 mbar_expect_tx(full, kABytes + b_bytes);
                 const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
                 const int kh = tap / p.taps_x, kw = tap - kh * p.taps_x;
-                tma_load_2d(sA + s * kABytes, &tmA, full, g * p.a_col_group + cb * kBK, m0 + kh * p.row_pitch + kw);
-                tma_load_2d(sB + s * b_bytes, &tmB, full, kb * kBK, g * p.b_row_group + n0);
+                tma_load_2d(sA + s * kABytes, &tmA, full, ge * p.a_col_group + cb * kBK, m0 + kh * p.row_pitch + kw);
+                tma_load_2d(sB + s * b_bytes, &tmB, full, kb * kBK, ge * p.b_row_group + n0);
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         const uint32_t idesc = umma_idesc_bf16(kBM, p.bn);
-        for (int i = 0; i < nkb; ++i) {
-            const int s = i % kStages;
-            const uint32_t ph = (uint32_t)(i / kStages) & 1u;
+        for (int it = 0; it < nkb * nfold; ++it) {
+            const int gi = it / nkb, i = it - gi * nkb;
+            const int s = it % kStages;
+            const uint32_t ph = (uint32_t)(it / kStages) & 1u;
             mbar_wait(smem_u32(&bar_full[s]), ph);
             tcgen05_fence_after();
             if (lane == 0) {
@@ -192,10 +200,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 for (int k = 0; k < kBK / 16; ++k) {
                     uint64_t ad = umma_desc_sw128(sA + s * kABytes + k * 32);
                     uint64_t bd = umma_desc_sw128(sB + s * b_bytes + k * 32);
-                    tcgen05_mma_bf16(tmem, ad, bd, idesc, (i | k) ? 1u : 0u);
+                    tcgen05_mma_bf16(tmem + (uint32_t)(gi * p.bn), ad, bd, idesc, (i | k) ? 1u : 0u);
                 }
                 tcgen05_commit(smem_u32(&bar_empty[s]));        // frees the smem stage when the MMAs retire
-                if (i == nkb - 1) tcgen05_commit(smem_u32(&bar_acc));
+                if (it == nkb * nfold - 1) tcgen05_commit(smem_u32(&bar_acc));
             }
             __syncwarp();
         }
@@ -215,6 +223,52 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         mbar_wait(smem_u32(&bar_acc), 0);
         tcgen05_fence_after();
         const int ccol0 = g * p.c_col_group + n0;
+        if (p.lrn) {
+            // Every thread owns one pixel with ALL its channels (the tile covers n_valid), so the cross-channel window is
+            // thread-local: walk the channels in chunks of 16 with the neighbouring two of the previous / next chunk.
+            const int nch = nfold * p.n_valid;                 // channels of the pixel (folded groups lie side by side in TMEM)
+            float prev0 = 0.f, prev1 = 0.f, cur[16], nxt[16];
+            auto load_chunk = [&](int c, float (&v)[16]) {
+                uint32_t r[16];
+                tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float x = __uint_as_float(r[j]);
+                    if (p.bias) x += __ldg(p.bias + g * p.n_valid + c + j);
+                    x = p.relu ? fmaxf(x, 0.f) : x;
+                    v[j] = (c + j < nch) ? x : 0.f;
+                }
+            };
+            load_chunk(0, cur);
+            for (int c = 0; c < nch; c += 16) {
+                const bool more = c + 16 < nch;
+                if (more) load_chunk(c + 16, nxt);
+                float sq[20];
+                sq[0] = prev0 * prev0; sq[1] = prev1 * prev1;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sq[2 + j] = cur[j] * cur[j];
+                sq[18] = more ? nxt[0] * nxt[0] : 0.f;
+                sq[19] = more ? nxt[1] * nxt[1] : 0.f;
+                if (valid) {
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float s0 = sq[2 * j] + sq[2 * j + 1] + sq[2 * j + 2] + sq[2 * j + 3] + sq[2 * j + 4];
+                        const float s1 = sq[2 * j + 1] + sq[2 * j + 2] + sq[2 * j + 3] + sq[2 * j + 4] + sq[2 * j + 5];
+                        const float y0 = cur[2 * j] * __powf(1.f + (1e-4f / 5.f) * s0, -0.75f);
+                        const float y1 = cur[2 * j + 1] * __powf(1.f + (1e-4f / 5.f) * s1, -0.75f);
+                        __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
+                        pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldc + ccol0 + c);
+                    o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+                prev0 = cur[14]; prev1 = cur[15];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+            }
+        } else
         for (int c = 0; c < p.bn; c += 16) {
             uint32_t r[16];
             tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
