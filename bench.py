@@ -282,7 +282,10 @@ def run_ours(args, rank, world, local_rank):
     # `depth` batches in flight: one library context + one host thread each (pipeline.StreamedPipeline); the serial
     # and the profiled legs use the first context alone
     depth = max(1, args.inflight)
-    sp = pipeline.StreamedPipeline(local_rank, ws, bs, depth=depth, sphere_mode=args.sphere_mode)
+    em_kw = {}
+    if args.num_init_vp is not None or args.config == 5:
+        em_kw["num_init_vp"] = args.num_init_vp if args.num_init_vp is not None else 32
+    sp = pipeline.StreamedPipeline(local_rank, ws, bs, depth=depth, sphere_mode=args.sphere_mode, **em_kw)
     pipe = sp.pipes[0]
     ctx = pipe.ctx
 
@@ -439,8 +442,14 @@ def run_ours(args, rank, world, local_rank):
         assert total_images == B_all
 
     if rank == 0:
-        # dominant kernel (largest share of the profiled steps) and its roofline
-        top = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else (None, None)
+        # Dominant kernel and its roofline.  `roofline_all` lists every kernel above 2 % of the profiled (serial) step by
+        # time.  The headline `roofline` is the largest of them that is throughput-bound by construction: em_post and em_init
+        # are one-CTA-per-image state machines (dependent L2 round trips and block barriers on at most one CTA per image;
+        # 64 registers, so other kernels share their SMs) -- with several batches in flight, the regime `value` is
+        # measured in, they overlap with the other batches' kernels and do not bound the throughput.
+        STATE_MACHINES = ("em_post", "em_init", "em_poste")
+        cands = {k: v for k, v in prof.items() if k not in STATE_MACHINES} or prof
+        top = max(cands.items(), key=lambda kv: kv[1]["ms"]) if cands else (None, None)
         roof = None
         n = np.diff(off).astype(np.float64)
 
@@ -493,6 +502,8 @@ def run_ours(args, rank, world, local_rank):
 
         if top[0] is not None:
             roof = roofline_of(*top)
+            roof["selection"] = ("largest kernel of the profiled step by time, one-CTA-per-image state machines (em_post, "
+                                 "em_init) excepted: latency-bound, they overlap with the other batches in flight")
         # the same figure for every kernel with a share of the step above 2 % (the headline `roofline` is the top one)
         tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
         roof_all = [roofline_of(k, v) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]) if v["ms"] > 0.02 * tot_ms]
@@ -543,7 +554,7 @@ def run_ours(args, rank, world, local_rank):
                        "segments_per_image_mean": float(np.mean(np.diff(off_all))),
                        "sphere_size": 500, "sphere_mode": args.sphere_mode, "cnn_weights": "random-init "
                        "(train_val.prototxt fillers x%g, seed 0)" % args.weight_scale,
-                       "batches_in_flight": depth,
+                       "batches_in_flight": depth, "num_init_vp": em_kw.get("num_init_vp", 25),
                        "l2": "each step streams > 1 GB of intermediates through the 126 MB L2 (inputs larger than L2); the "
                              "serial and profiled legs also flush it between steps (256 MiB memset)",
                        "parallelism": ("ONE batch sharded over the ranks (pipeline.shard_batch: LPT on N^2 + const), no data-path "
@@ -593,6 +604,8 @@ def main():
     ap.add_argument("--strong", action="store_true", help="shard ONE batch over the ranks (default for --gpus > 1)")
     ap.add_argument("--weak", action="store_true", help="every rank runs its own copy of the batch")
     ap.add_argument("--no-reference-em", action="store_true", help="skip the reference's own EM in the CPU baseline")
+    ap.add_argument("--num-init-vp", type=int, default=None,
+                    help="EM hypotheses per image (default 25, vp_localisation.py:170; 32 for the stress config 5)")
     ap.add_argument("--inflight", type=int, default=3, help="batches in flight per GPU (library contexts + host threads)")
     ap.add_argument("--images", type=int, default=None, help="override the number of images per GPU")
     ap.add_argument("--sphere-mode", default="votes", choices=["votes", "curves"])
