@@ -512,7 +512,7 @@ __device__ __forceinline__ void wmat_pass(WSmemT<kStages>& sm, const double* sla
 // keep: the similarity matrices of the slots still active fit the L2, so they are loaded with the
 // default policy and stay resident from one superstep to the next (evict-first otherwise).
 template <int kStages>
-__global__ void __launch_bounds__(kWThreads, 2) em_wmat_kernel(EmParams P, int csl, int keep) {
+__global__ void __launch_bounds__(kWThreads, 2) em_wmat_kernel(EmParams P, int csl, int keep, int want_split) {
     extern __shared__ __align__(128) unsigned char w_smem_raw[];
     WSmemT<kStages>& sm = *reinterpret_cast<WSmemT<kStages>*>(w_smem_raw);
     const int cur = P.ctl[3] & 1;
@@ -522,6 +522,9 @@ __global__ void __launch_bounds__(kWThreads, 2) em_wmat_kernel(EmParams P, int c
     if (!st.run_w) return;
     const int N = st.N, M = st.M, t = blockIdx.x / csl;
     if (t * kTK >= N) return;                       // uniform over the cluster
+    // Tall slabs (N > 1536) are shared by the CTAs of a cluster, all others take one CTA: two launches per superstep,
+    // each skipping the other's slots, so that no idle cluster rank holds shared memory next to a short slab.
+    if ((wmat_split(N) > 1) != (want_split != 0)) return;
     const int rank = csl > 1 ? (int)em_cluster_ctarank() : 0;
     const int cs = min(wmat_split(N), csl);         // CTAs of the cluster that share this slab
     const Img im = make_img(N, P.ws + st.ws_off, P.segs + 4 * (size_t)st.base);
@@ -984,7 +987,7 @@ __global__ void __launch_bounds__(256) em_distribution_kernel(const EmSlot* __re
 // active (POST sets the conditions), so neither the host nor empty CTAs sit on the critical path.
 struct EmLoopGraph {
     EmParams key;
-    int n = 0, nmax = 0;
+    int n = 0, nmax = 0, nbig = 0;
     int supersteps_per_iter = 0;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
@@ -1002,7 +1005,7 @@ constexpr int kMaxGroups = 8;
 constexpr int kPosteCluster = 4;      // CTAs per image of em_poste (408 CTAs for the 102 images of the YUD batch: one wave)
 constexpr int kGroupSlots = 26;       // images per group (default; VPK_EM_GROUPS overrides the group count)
 
-struct GroupRun { EmParams P; cudaStream_t s; int n, nmax, csl, bound, step; bool done; };
+struct GroupRun { EmParams P; cudaStream_t s; int n, nmax, nbig, bound, step; bool done; };
 enum { MODE_FUSED = 0, MODE_GRAPH = 1, MODE_HOST = 2 };
 struct EmWave {
     bool begun = false;                    // wave_begin done, wave_run pending
@@ -1058,33 +1061,37 @@ static bool use_poste() {
 }
 
 // one superstep on the stream (direct launch or stream capture): E -> W -> POST over `bound` slots
-static int enqueue_superstep(vpk_ctx* ctx, cudaStream_t sm, const EmParams& P, int bound, int nmax, int csl, const TierCtl& tc,
-                             bool scoped) {
-    const int tiles = (nmax + kTK - 1) / kTK;
+// nbig: slots of the group whose slabs are split over a cluster (N > 1536); they are the first slots of the group
+// (heaviest first), hence the first entries of every active list.
+static int enqueue_superstep(vpk_ctx* ctx, cudaStream_t sm, const EmParams& P, int bound, int nmax, int nbig, int n_group,
+                             const TierCtl& tc, bool scoped) {
     const bool poste = use_poste();
     if (!poste) {
         KernelScope ks(ctx, "em_estep", scoped);
         em_estep_kernel<<<dim3((nmax + kEL - 1) / kEL, bound), kEThreads, 0, sm>>>(P);
         VPK_TRY(check_launch("em_estep"));
     }
-    {
+    auto launch_w = [&](int csl, int slots, int n_cols, int want_split) -> int {
         KernelScope ks(ctx, "em_wmat", scoped);
+        const int tiles = (n_cols + kTK - 1) / kTK;
         cudaLaunchConfig_t lc = {};
-        lc.gridDim = dim3(tiles * csl, bound);
+        lc.gridDim = dim3(tiles * csl, slots);
         lc.blockDim = dim3(kWThreads);
         // fewer CTAs than SMs: deeper ring; similarity matrices of the active slots within half the L2: keep them there
-        const bool tail = (long long)tiles * csl * bound <= (long long)ctx->num_sms;
-        const int keep = 8.0 * nmax * nmax * bound <= 0.5 * (double)ctx->l2_bytes ? 1 : 0;
+        const bool tail = (long long)tiles * csl * slots <= (long long)ctx->num_sms;
+        const int keep = 8.0 * n_cols * n_cols * slots <= 0.5 * (double)ctx->l2_bytes ? 1 : 0;
         lc.dynamicSmemBytes = tail ? sizeof(WSmemT<kStagesTail>) : sizeof(WSmemT<kStages>);
         lc.stream = sm;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = csl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         lc.attrs = at; lc.numAttrs = 1;
-        if (tail) VPK_CUDA(cudaLaunchKernelEx(&lc, em_wmat_kernel<kStagesTail>, P, csl, keep));
-        else VPK_CUDA(cudaLaunchKernelEx(&lc, em_wmat_kernel<kStages>, P, csl, keep));
-        VPK_TRY(check_launch("em_wmat"));
-    }
+        if (tail) VPK_CUDA(cudaLaunchKernelEx(&lc, em_wmat_kernel<kStagesTail>, P, csl, keep, want_split));
+        else VPK_CUDA(cudaLaunchKernelEx(&lc, em_wmat_kernel<kStages>, P, csl, keep, want_split));
+        return check_launch("em_wmat");
+    };
+    if (nbig > 0) VPK_TRY(launch_w(wmat_split(nmax), std::min(bound, nbig), nmax, 1));
+    if (nbig < n_group) VPK_TRY(launch_w(1, bound, std::min(nmax, 1536), 0));
     if (!poste) {
         KernelScope ks(ctx, "em_post", scoped);
         em_post_kernel<<<bound, kPostThreads, 0, sm>>>(P, tc);
@@ -1115,9 +1122,8 @@ static int enqueue_first_estep(vpk_ctx* ctx, cudaStream_t sm, const EmParams& P,
     return check_launch("em_estep");
 }
 
-static int build_loop_graph(vpk_ctx* ctx, cudaStream_t sm, EmLoopGraph& G, const EmParams& P, int n, int nmax, int max_steps) {
+static int build_loop_graph(vpk_ctx* ctx, cudaStream_t sm, EmLoopGraph& G, const EmParams& P, int n, int nmax, int nbig, int max_steps) {
     G.destroy();
-    const int csl = wmat_split(nmax);
     VPK_CUDA(cudaGraphCreate(&G.graph, 0));
     TierCtl tc;
     memset(&tc, 0, sizeof(tc));
@@ -1143,7 +1149,7 @@ static int build_loop_graph(vpk_ctx* ctx, cudaStream_t sm, EmLoopGraph& G, const
         VPK_CUDA(cudaGraphAddNode(&node, G.graph, prev ? &prev : nullptr, prev ? 1 : 0, &np));
         cudaGraph_t body = np.conditional.phGraph_out[0];
         VPK_CUDA(cudaStreamBeginCaptureToGraph(sm, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
-        int rc = enqueue_superstep(ctx, sm, P, bound[j], nmax, csl, tc, false);
+        int rc = enqueue_superstep(ctx, sm, P, bound[j], nmax, nbig, n, tc, false);
         cudaGraph_t dummy = nullptr;
         cudaError_t e = cudaStreamEndCapture(sm, &dummy);
         if (rc != VPK_OK) return rc;
@@ -1151,7 +1157,7 @@ static int build_loop_graph(vpk_ctx* ctx, cudaStream_t sm, EmLoopGraph& G, const
         prev = node;
     }
     VPK_CUDA(cudaGraphInstantiate(&G.exec, G.graph, 0));
-    G.key = P; G.n = n; G.nmax = nmax;
+    G.key = P; G.n = n; G.nmax = nmax; G.nbig = nbig;
     return VPK_OK;
 }
 
@@ -1221,17 +1227,18 @@ static int plan_wave(vpk_ctx* ctx, EmState* st, const EmParams& P0, const int32_
     for (int g = 0; g < G; ++g) {
         GroupRun& r = W.R[g];
         const int g0 = i;
-        r.nmax = 1;
+        r.nmax = 1; r.nbig = 0;
         for (int k = g; k < n; k += G, ++i) {
             const int b = W.order[begin + k];
             hd[i].img = b; hd[i].base = h_offsets[b]; hd[i].N = h_offsets[b + 1] - h_offsets[b]; hd[i].pad = 0;
             hd[i].ws_off = off;
             off += slot_doubles(hd[i].N);
             r.nmax = std::max(r.nmax, hd[i].N);
+            r.nbig += wmat_split(hd[i].N) > 1 ? 1 : 0;
         }
         r.s = ctx->profiling ? ctx->stream : st->gstream[g];
         memcpy(&r.P, &P, sizeof(EmParams));      // padding included: the loop graph is keyed on the bytes
-        r.n = i - g0; r.csl = wmat_split(r.nmax); r.bound = r.n; r.step = 0; r.done = false;
+        r.n = i - g0; r.bound = r.n; r.step = 0; r.done = false;
         r.P.slots = P.slots + g0; r.P.desc = P.desc + g0; r.P.lists = P.lists + 2 * (size_t)g0; r.P.alive = P.alive + g0;
         r.P.ctl = P.ctl + g * kCtlInts; r.P.n_slots = r.n;
     }
@@ -1324,8 +1331,8 @@ static int wave_run(vpk_ctx* ctx, EmState* st) {
         if (W.mode != MODE_FUSED && use_poste()) VPK_TRY(enqueue_first_estep(ctx, r.s, r.P, r.n, r.nmax));
         if (W.device_loop) {
             EmLoopGraph& L = *st->loop[g];
-            if (!L.exec || L.n != r.n || L.nmax != r.nmax || memcmp(&L.key, &r.P, sizeof(EmParams)) != 0) {
-                VPK_TRY(build_loop_graph(ctx, r.s, L, r.P, r.n, r.nmax, max_steps));
+            if (!L.exec || L.n != r.n || L.nmax != r.nmax || L.nbig != r.nbig || memcmp(&L.key, &r.P, sizeof(EmParams)) != 0) {
+                VPK_TRY(build_loop_graph(ctx, r.s, L, r.P, r.n, r.nmax, r.nbig, max_steps));
                 ++rebuilt;
             }
             VPK_CUDA(cudaGraphLaunch(L.exec, r.s));
@@ -1342,7 +1349,7 @@ static int wave_run(vpk_ctx* ctx, EmState* st) {
         VPK_CUDA(cudaStreamSynchronize(sm));
         for (int g = 0; g < G; ++g) {
             const int* c = h_cnt + g * kCtlInts;
-            ctx->launches += (use_poste() ? 2 : 3) * (int64_t)c[3];
+            ctx->launches += ((use_poste() ? 2 : 3) + ((W.R[g].nbig > 0 && W.R[g].nbig < W.R[g].n) ? 1 : 0)) * (int64_t)c[3];
             steps = std::max(steps, c[3]);
             if (c[5]) { set_error("vpk_em: supersteps did not terminate"); return VPK_ERR_STATE; }
         }
@@ -1368,7 +1375,7 @@ static int wave_run(vpk_ctx* ctx, EmState* st) {
                     }
                 }
                 for (int k = 0; k < kChunkSteps; ++k, ++r.step)
-                    VPK_TRY(enqueue_superstep(ctx, r.s, r.P, r.bound, r.nmax, r.csl, tc, true));
+                    VPK_TRY(enqueue_superstep(ctx, r.s, r.P, r.bound, r.nmax, r.nbig, r.n, tc, true));
                 // length of the list the next superstep will read
                 VPK_CUDA(cudaMemcpyAsync(ring + (chunk & 7), r.P.ctl + (r.step & 1), sizeof(int), cudaMemcpyDeviceToHost, r.s));
                 VPK_CUDA(cudaEventRecord(st->gev[g][chunk & 7], r.s));
