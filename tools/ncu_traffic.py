@@ -46,10 +46,8 @@ def main():
             add(GEMMS[gi], byt, ms, grid); gi += 1
         elif "splitk" in name:
             add(SPLITK[si], byt, ms, grid); si += 1
-        elif "lrn_pool_kernel<1>" in name:
-            add(["lrn_pool1", "lrn_pool2"][li], byt, ms, grid); li += 1
-        elif "lrn_pool_kernel<0>" in name:
-            add("pool5", byt, ms, grid)
+        elif "lrn_pool_kernel" in name:           # the three max-pools, in launch order (the LRN lives in the conv epilogues)
+            add(["pool1", "pool2", "pool5"][min(li, 2)], byt, ms, grid); li += 1
         else:
             add(name.replace("void ", "").split("<")[0].replace("_kernel", ""), byt, ms, grid)
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
