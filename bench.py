@@ -264,8 +264,12 @@ def run_ours(args, rank, world, local_rank):
     from vanishing_points_2017_b200 import cnn as vcnn, pipeline
 
     torch.cuda.set_device(local_rank)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # the result gather runs over host memory (gloo): the results are on the host when a step returns and the GPU's
+        # streams are busy with the next batches -- no NCCL on the path (north_star)
+        host_group = dist.new_group(backend="gloo")
     peaks = load_peaks()
     name, seg_all, off_all = make_workload(args.config, 0, args.images)
     B_all = len(off_all) - 1
@@ -396,7 +400,7 @@ def run_ours(args, rank, world, local_rank):
             if gather:
                 # the path's only exchange: the per-image results of every shard end up on rank 0
                 tg = time.perf_counter()
-                full_ = pipeline.gather_raw(last, off_all, world, rank, dist)
+                full_ = pipeline.gather_raw(last, off_all, world, rank, dist, group=host_group)
                 gms += (time.perf_counter() - tg) * 1e3
         return last, full_, gms
 

@@ -246,12 +246,14 @@ def _blob_layout(n_img, n_seg):
     return lay, pos
 
 
-def gather_raw(arrs, offsets_all, world_size, rank, dist=None):
+def gather_raw(arrs, offsets_all, world_size, rank, dist=None, group=None):
     """The path's only inter-rank exchange, for the flat result arrays (`raw=True`) of the shards
     `shard_batch(offsets_all, world_size, r)`: ONE fixed-size `torch.distributed.gather` of a byte blob per rank
     (every rank can compute every shard's sizes from the batch offsets, so nothing else is exchanged; NCCL moves
-    the blobs over NVLink, gloo over sockets in the CPU tests).  Rank 0 returns the arrays reassembled in the
-    batch's image order plus "offsets" (the batch's prefix sums, for vp_assoc); the other ranks return None."""
+    the blobs over NVLink, gloo over sockets / shared memory; `group`: the process group to use -- the results are
+    in host memory when a step returns, so a gloo group keeps the exchange off the GPU, whose streams are busy with
+    the next batches).  Rank 0 returns the arrays reassembled in the batch's image order plus "offsets" (the batch's
+    prefix sums, for vp_assoc); the other ranks return None."""
     import torch
     offsets_all = np.asarray(offsets_all, dtype=np.int64)
     n_all = np.diff(offsets_all)
@@ -260,7 +262,7 @@ def gather_raw(arrs, offsets_all, world_size, rank, dist=None):
     sizes = [(len(ix), int(n_all[ix].sum())) for ix in shards]
     layouts = [_blob_layout(*sz) for sz in sizes]
     nbytes = max(l[1] for l in layouts)
-    use_cuda = dist is not None and world_size > 1 and dist.get_backend() == "nccl"
+    use_cuda = dist is not None and world_size > 1 and dist.get_backend(group) == "nccl"
     key = (nbytes, world_size, rank, use_cuda)
     buf = _gather_cache.get(key)
     if buf is None:
@@ -289,7 +291,7 @@ def gather_raw(arrs, offsets_all, world_size, rank, dist=None):
     elif use_cuda:
         buf["dev"].copy_(buf["host"], non_blocking=True)
         parts = list(buf["dev_all"].view(world_size, nbytes).unbind(0)) if rank == 0 else None
-        dist.gather(buf["dev"], parts, dst=0)
+        dist.gather(buf["dev"], parts, dst=0, group=group)
         if rank != 0:
             return None
         buf["host_all"].copy_(buf["dev_all"], non_blocking=True)
@@ -297,7 +299,7 @@ def gather_raw(arrs, offsets_all, world_size, rank, dist=None):
         allv = buf["host_all"].numpy().reshape(world_size, nbytes)
     else:
         parts = list(buf["host_all"].view(world_size, nbytes).unbind(0)) if rank == 0 else None
-        dist.gather(buf["host"], parts, dst=0)
+        dist.gather(buf["host"], parts, dst=0, group=group)
         if rank != 0:
             return None
         allv = buf["host_all"].numpy().reshape(world_size, nbytes)
