@@ -390,11 +390,15 @@ def run_ours(args, rank, world, local_rank):
     # ---- end-to-end leg from pinned host buffers -> `e2e`: every step is one public-API call (H2D, path, D2H), `depth`
     # calls in flight; with several ranks the results of every step are then gathered on rank 0 (in step order, on this
     # thread).  Wall clock between two barriers: host work, copies and the gather are all inside.
+    e2e_wait = [0.0]
+
     def e2e_steps(n_steps, seg_h, off_h, gather):
         gms, last, full_ = 0.0, None, None
         futs = [sp.submit(seg_h, off_h, raw=True) for _ in range(min(depth, n_steps))]
         for i in range(n_steps):
+            tw = time.perf_counter()
             last = futs[i % depth].result()
+            e2e_wait[0] += (time.perf_counter() - tw) * 1e3
             if i + depth < n_steps:
                 futs[i % depth] = sp.submit(seg_h, off_h, raw=True)
             if gather:
@@ -407,8 +411,10 @@ def run_ours(args, rank, world, local_rank):
     do_gather = args.strong and world > 1
     e2e_steps(max(depth, args.warmup // 2), seg_pin.numpy(), off_pin.numpy(), do_gather)
     barrier()
+    e2e_wait[0] = 0.0
     t0 = time.perf_counter()
     out, full, gather_ms = e2e_steps(args.steps, seg_pin.numpy(), off_pin.numpy(), do_gather)
+    wait_ms = e2e_wait[0] / args.steps
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     clocks = sampler.summary()            # sampled over both timed legs (and the profiled leg between them)
@@ -417,7 +423,7 @@ def run_ours(args, rank, world, local_rank):
     n_ok_all = None
     if args.strong and world > 1 and rank == 0:
         n_ok_all = int(np.sum(full["status"] == 0))
-        assert full["status"].shape[0] == B_all and int(full["offsets"][-1]) == int(off_all[-1])
+        assert full["status"].shape[0] == B_all and full["vp_assoc"].shape[0] == int(off_all[-1])
 
     # ---- strong scaling: the one-GPU figure of the SAME batch, measured by rank 0 in this very run
     one_gpu = None
@@ -571,7 +577,8 @@ def run_ours(args, rank, world, local_rank):
                 "speedup_e2e": (total_images / (e2e_step * 1e-3)) / one_gpu["e2e_images_per_s"] if one_gpu else None,
                 "rank_time_ms": {"resident_max": ms_step, "resident_min": float(tmin[0].item()),
                                  "e2e_max": e2e_step, "e2e_min": float(tmin[1].item())},
-                "gather_ms_per_step_rank0": gather_ms / args.steps, "images_with_vps_after_gather": n_ok_all},
+                "gather_ms_per_step_rank0": gather_ms / args.steps, "wait_for_own_shard_ms_per_step_rank0": wait_ms,
+                "images_with_vps_after_gather": n_ok_all},
             "serial": {"value": total_images / (serial_step * 1e-3), "unit": UNIT, "ms_per_step": serial_step,
                        "what": "one batch at a time on one context, L2 flushed between steps (the latency of a batch; "
                                "`stages_ms_per_step` and `step_ms` are of this leg)"},

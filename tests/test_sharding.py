@@ -112,13 +112,17 @@ def test_gather_raw_gloo_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     n_all = np.array([30, 0, 75, 12, 51, 9, 64])
-    np.testing.assert_array_equal(out["offsets"], np.concatenate([[0], np.cumsum(n_all)]))
+    np.testing.assert_array_equal(out["n"], n_all)
     np.testing.assert_array_equal(out["iterations"], np.arange(7) * 2)
     np.testing.assert_array_equal(out["vp"][:, 0, 0], np.arange(7.0))
-    np.testing.assert_array_equal(out["vp_assoc"], np.repeat(np.arange(7), n_all))
+    assert out["vp_assoc"].shape[0] == n_all.sum()
+    for i in range(7):              # image i owns vp_assoc[assoc_start[i] : assoc_start[i] + n[i]] (rank-major order)
+        a = out["assoc_start"][i]
+        np.testing.assert_array_equal(out["vp_assoc"][a:a + n_all[i]], np.full(n_all[i], i))
     np.testing.assert_array_equal(out["n_vp"], np.arange(7) % 5 + 1)
     # single rank: the identity
     arrs, off = _fake_raw(np.array([0, 1, 2]), np.array([3, 4, 5]))
     one = pipeline.gather_raw(arrs, off, 1, 0)
     np.testing.assert_array_equal(one["vp_assoc"], np.repeat([0, 1, 2], [3, 4, 5]))
+    np.testing.assert_array_equal(one["assoc_start"], [0, 3, 7])
     np.testing.assert_array_equal(one["vp"][:, 0, 1], np.arange(3) + 0.5)

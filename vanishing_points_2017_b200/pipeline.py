@@ -246,22 +246,44 @@ def _blob_layout(n_img, n_seg):
     return lay, pos
 
 
+_plan_cache = {}
+
+
+def _gather_plan(offsets_all, world_size):
+    """Everything about a sharded batch that does not change from step to step (cached on the offsets)."""
+    offsets_all = np.ascontiguousarray(offsets_all, dtype=np.int64)
+    key = (offsets_all.tobytes(), world_size)
+    plan = _plan_cache.get(key)
+    if plan is None:
+        n_all = np.diff(offsets_all)
+        shards = [shard_batch(offsets_all, world_size, r) for r in range(world_size)]
+        sizes = [(len(ix), int(n_all[ix].sum())) for ix in shards]
+        layouts = [_blob_layout(*sz) for sz in sizes]
+        # vp_assoc stays in rank-major order (the blobs as they arrive); image i starts at assoc_start[i]
+        assoc_start = np.empty(n_all.shape[0], dtype=np.int64)
+        base = 0
+        for ix, (_, n_seg) in zip(shards, sizes):
+            assoc_start[ix] = base + np.concatenate([[0], np.cumsum(n_all[ix])])[:-1]
+            base += n_seg
+        plan = {"n": n_all, "shards": shards, "sizes": sizes, "layouts": layouts, "assoc_start": assoc_start,
+                "nbytes": max(l[1] for l in layouts)}
+        _plan_cache.clear()
+        _plan_cache[key] = plan
+    return plan
+
+
 def gather_raw(arrs, offsets_all, world_size, rank, dist=None, group=None):
     """The path's only inter-rank exchange, for the flat result arrays (`raw=True`) of the shards
     `shard_batch(offsets_all, world_size, r)`: ONE fixed-size `torch.distributed.gather` of a byte blob per rank
-    (every rank can compute every shard's sizes from the batch offsets, so nothing else is exchanged; NCCL moves
-    the blobs over NVLink, gloo over sockets / shared memory; `group`: the process group to use -- the results are
-    in host memory when a step returns, so a gloo group keeps the exchange off the GPU, whose streams are busy with
-    the next batches).  Rank 0 returns the arrays reassembled in the batch's image order plus "offsets" (the batch's
-    prefix sums, for vp_assoc); the other ranks return None."""
+    (every rank can compute every shard's sizes from the batch offsets, so nothing else is exchanged; `group`: the
+    process group to use -- the results are in host memory when a step returns, so a gloo group keeps the exchange
+    off the GPU, whose streams are busy with the next batches; with an NCCL group the blobs go over NVLink).
+    Rank 0 returns the per-image arrays in the batch's image order, "vp_assoc" in rank-major order with
+    "assoc_start" (image i owns vp_assoc[assoc_start[i] : assoc_start[i] + n[i]]) and "n"; the other ranks None."""
     import torch
-    offsets_all = np.asarray(offsets_all, dtype=np.int64)
-    n_all = np.diff(offsets_all)
-    n_images = n_all.shape[0]
-    shards = [shard_batch(offsets_all, world_size, r) for r in range(world_size)]
-    sizes = [(len(ix), int(n_all[ix].sum())) for ix in shards]
-    layouts = [_blob_layout(*sz) for sz in sizes]
-    nbytes = max(l[1] for l in layouts)
+    plan = _gather_plan(offsets_all, world_size)
+    shards, sizes, layouts, nbytes = plan["shards"], plan["sizes"], plan["layouts"], plan["nbytes"]
+    n_images = plan["n"].shape[0]
     use_cuda = dist is not None and world_size > 1 and dist.get_backend(group) == "nccl"
     key = (nbytes, world_size, rank, use_cuda)
     buf = _gather_cache.get(key)
@@ -303,21 +325,18 @@ def gather_raw(arrs, offsets_all, world_size, rank, dist=None, group=None):
         if rank != 0:
             return None
         allv = buf["host_all"].numpy().reshape(world_size, nbytes)
-    # reassemble in image order (vectorised: no per-image Python work)
+    # per-image arrays in image order; the line associations stay where they arrived
     out = {k: np.empty((n_images,) + _RAW_TAIL[k], dtype=_RAW_DTYPES[k]) for k in RAW_PER_IMAGE}
-    out["vp_assoc"] = np.empty(int(offsets_all[-1]), dtype=np.int32)
-    out["offsets"] = offsets_all
+    assoc = []
     for r in range(world_size):
         lay, _ = layouts[r]
-        ix = shards[r]
         n_img, n_seg = sizes[r]
         for k in RAW_PER_IMAGE:
             pos, nb = lay[k]
-            out[k][ix] = allv[r, pos:pos + nb].view(_RAW_DTYPES[k]).reshape((n_img,) + _RAW_TAIL[k])
+            out[k][shards[r]] = allv[r, pos:pos + nb].view(_RAW_DTYPES[k]).reshape((n_img,) + _RAW_TAIL[k])
         pos, nb = lay["vp_assoc"]
-        part = allv[r, pos:pos + nb].view(np.int32)
-        n_r = n_all[ix]
-        local_start = np.concatenate([[0], np.cumsum(n_r)])[:-1]
-        dest = np.repeat(offsets_all[ix] - local_start, n_r) + np.arange(n_seg)
-        out["vp_assoc"][dest] = part
+        assoc.append(allv[r, pos:pos + nb].view(np.int32))
+    out["vp_assoc"] = np.concatenate(assoc) if len(assoc) > 1 else assoc[0].copy()
+    out["assoc_start"] = plan["assoc_start"]
+    out["n"] = plan["n"]
     return out
