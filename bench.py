@@ -391,9 +391,17 @@ def run_ours(args, rank, world, local_rank):
     # calls in flight; with several ranks the results of every step are then gathered on rank 0 (in step order, on this
     # thread).  Wall clock between two barriers: host work, copies and the gather are all inside.
     e2e_wait = [0.0]
+    from concurrent.futures import ThreadPoolExecutor
+    gather_pool = ThreadPoolExecutor(max_workers=1)      # ONE thread: every rank issues its gathers in step order
+
+    def gather_step(res):
+        # the path's only exchange: the per-image results of every shard end up on rank 0
+        tg = time.perf_counter()
+        full_ = pipeline.gather_raw(res, off_all, world, rank, dist, group=host_group)
+        return full_, (time.perf_counter() - tg) * 1e3
 
     def e2e_steps(n_steps, seg_h, off_h, gather):
-        gms, last, full_ = 0.0, None, None
+        last, gfuts = None, []
         futs = [sp.submit(seg_h, off_h, raw=True) for _ in range(min(depth, n_steps))]
         for i in range(n_steps):
             tw = time.perf_counter()
@@ -402,11 +410,9 @@ def run_ours(args, rank, world, local_rank):
             if i + depth < n_steps:
                 futs[i % depth] = sp.submit(seg_h, off_h, raw=True)
             if gather:
-                # the path's only exchange: the per-image results of every shard end up on rank 0
-                tg = time.perf_counter()
-                full_ = pipeline.gather_raw(last, off_all, world, rank, dist, group=host_group)
-                gms += (time.perf_counter() - tg) * 1e3
-        return last, full_, gms
+                gfuts.append(gather_pool.submit(gather_step, last))     # off the submit loop; completed inside the timed region
+        done = [g.result() for g in gfuts]
+        return last, (done[-1][0] if done else None), sum(d[1] for d in done)
 
     do_gather = args.strong and world > 1
     e2e_steps(max(depth, args.warmup // 2), seg_pin.numpy(), off_pin.numpy(), do_gather)
