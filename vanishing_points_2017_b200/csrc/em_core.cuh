@@ -318,10 +318,12 @@ VPK_DEV SegPre seg_pre(const Seg& s) {
 }
 VPK_DEV double psd2_pre(const SegPre& s, double px, double py) {
     const double param = ((px - s.x1) * s.dx + (py - s.y1) * s.dy) * s.inv_nn;
-    double cx, cy;
-    if (param < 0) { cx = s.x1; cy = s.y1; }
-    else if (param > 1) { cx = s.x2; cy = s.y2; }
-    else { cx = s.x1 + param * s.dx; cy = s.y1 + param * s.dy; }
+    // branch-free: the interior point is always formed and replaced by an end point outside [0, 1] (same values as
+    // the reference's if / elif / else, :750-756; a NaN parameter takes the interior expression like the reference)
+    double cx = s.x1 + param * s.dx, cy = s.y1 + param * s.dy;
+    const bool lo = param < 0, hi = param > 1;
+    cx = hi ? s.x2 : cx; cy = hi ? s.y2 : cy;
+    cx = lo ? s.x1 : cx; cy = lo ? s.y1 : cy;
     const double ex = cx - px, ey = cy - py;
     return ex * ex + ey * ey;
 }
@@ -335,10 +337,11 @@ VPK_DEV double seg_distance2(const SegPre& a, const SegPre& b) {
 VPK_DEV double cos9_pre(const SegPre& a, const SegPre& b) {
     double c = fabs((a.dx * b.dx + a.dy * b.dy) * (a.inv_len * b.inv_len));
     c = c > 1.0 ? 1.0 : c;                 // NaN stays NaN
-    if (c <= 0.984807753012208) return 6.123233995736766e-17;
+    // branch-free (nine of ten pairs are clipped, so nearly every warp would run both sides of a branch anyway)
     const double t = c * (4.0 * c * c - 3.0);
-    const double r = t * (4.0 * t * t - 3.0);
-    return r < 6.123233995736766e-17 ? 6.123233995736766e-17 : r;
+    double r = t * (4.0 * t * t - 3.0);
+    r = r < 6.123233995736766e-17 ? 6.123233995736766e-17 : r;
+    return c <= 0.984807753012208 ? 6.123233995736766e-17 : r;
 }
 VPK_DEV double prox_pre(const SegPre& a, const SegPre& b, double d2) { return exp(-(d2 * fmax(a.h, b.h))); }
 // lines_similarity (:700-705) from the squared distance
