@@ -23,7 +23,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 struct CnnState {
     bool loaded = false;
-    bool attr3 = false, attr4 = false;     // dynamic shared-memory opt-in of the two GEMM instantiations: per CONTEXT (device)
+    bool attr2 = false, attr3 = false, attr4 = false;     // dynamic shared-memory opt-in of the two GEMM instantiations: per CONTEXT (device)
     EncodeTiledFn encode = nullptr;
     // bf16 weight matrices (K-major) and fp32 biases, one per layer conv1..fc8
     DBuf w[8], b[8], mean;
@@ -257,7 +257,13 @@ int launch_gemm(vpk_ctx* ctx, const GemmCall& c) {
     dim3 grid(m_tiles, n_tiles, (c.groups / fold) * ksplit);
     const size_t stage = kABytes + (size_t)c.p.bn * kBK * 2;
     KernelScope ks(ctx, c.name);
-    if (c.p.bn <= 128) {
+    if (c.p.bn <= 128 && c.p.k_blocks * fold <= 3) {
+        // very short K loops (conv1: 3 blocks): latency bound per CTA, so two stages and three CTAs per SM
+        size_t smem = 2 * stage + 1024;
+        bool& attr2 = st->attr2;
+        if (!attr2) { VPK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (kABytes + 128 * kBK * 2) + 1024)); attr2 = true; }
+        gemm_bf16_tcgen05_kernel<2><<<grid, kGemmThreads, smem, ctx->stream>>>(ma, mb, c.p);
+    } else if (c.p.bn <= 128) {
         size_t smem = 3 * stage + 1024;
         bool& attr3 = st->attr3;
         if (!attr3) { VPK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (kABytes + 128 * kBK * 2) + 1024)); attr3 = true; }

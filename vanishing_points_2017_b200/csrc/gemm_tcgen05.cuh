@@ -23,7 +23,8 @@
 
 namespace vpk {
 
-static constexpr int kGemmThreads = 192;       // warp0 TMA, warp1 MMA/TMEM, warps 2-5 epilogue
+static constexpr int kGemmThreads = 320;       // warp0 TMA, warp1 MMA/TMEM, warps 2-9 epilogue (two per TMEM lane quarter,
+                                               // each taking half of the tile's columns)
 static constexpr int kBM = 128;                // UMMA_M (cta_group::1)
 static constexpr int kBK = 64;                 // bf16 per 128-byte swizzle row
 static constexpr int kABytes = kBM * kBK * 2;  // 16 KiB per stage
@@ -210,6 +211,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     } else {
         // ===== epilogue: TMEM -> registers -> bias/ReLU -> global =====
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
+        const int half = (warp - 2) >> 2;             // which half of the tile's columns this warp writes
         const int row = quarter * 32 + lane;
         const int m = m0 + row;
         bool valid = m < p.m_total;
@@ -227,6 +229,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             // Every thread owns one pixel with ALL its channels (the tile covers n_valid), so the cross-channel window is
             // thread-local: walk the channels in chunks of 16 with the neighbouring two of the previous / next chunk.
             const int nch = nfold * p.n_valid;                 // channels of the pixel (folded groups lie side by side in TMEM)
+            const int cmid = ((nch / 16 + 1) / 2) * 16;        // this warp normalises the channels [cb, ce) and peeks two beyond each end
+            const int cb = half ? cmid : 0, ce = half ? nch : cmid;
             float prev0 = 0.f, prev1 = 0.f, cur[16], nxt[16];
             auto load_chunk = [&](int c, float (&v)[16]) {
                 uint32_t r[16];
@@ -239,8 +243,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     v[j] = (c + j < nch) ? x : 0.f;
                 }
             };
-            load_chunk(0, cur);
-            for (int c = 0; c < nch; c += 16) {
+            if (cb > 0) { load_chunk(cb - 16, cur); prev0 = cur[14]; prev1 = cur[15]; }
+            load_chunk(cb, cur);
+            for (int c = cb; c < ce; c += 16) {
                 const bool more = c + 16 < nch;
                 if (more) load_chunk(c + 16, nxt);
                 float sq[20];
@@ -269,7 +274,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
             }
         } else
-        for (int c = 0; c < p.bn; c += 16) {
+        for (int c = half ? ((p.bn / 16 + 1) / 2) * 16 : 0; c < (half ? p.bn : ((p.bn / 16 + 1) / 2) * 16); c += 16) {
             uint32_t r[16];
             tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
             if (!valid || n0 + c >= p.n_valid) continue;
