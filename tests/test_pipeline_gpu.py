@@ -102,3 +102,23 @@ def test_streamed_pipeline_keeps_batches_in_flight_and_equals_the_serial_results
     c0.mark(0); c1.mark(1)
     assert c0.elapsed_ms(0, c1, 1) >= 0.0
     c0.close(); c1.close()
+
+
+def test_pipeline_defaults_to_the_reference_line_plot_when_weights_are_given(pipe):
+    """With weights supplied and no sphere_mode, the pipeline feeds the CNN what the trained net expects: the
+    great-circle line plot of sphere_mapping.sphere_line_plot (sphere_mapping.py:36-72), not the vote histogram."""
+    from vanishing_points_2017_b200 import _lib, pipeline
+    _, ws, bs = pipe
+    p = pipeline.Pipeline(0, ws, bs, ctx=_lib.Context(0))
+    try:
+        assert p.mode == _lib.SPHERE_CURVES
+        batch = synth.make_batch(2, n_images=3)
+        res, sig, sph = p(batch["segments"], batch["offsets"], want_response=True, want_sphere=True)
+        off = batch["offsets"]
+        for b in range(3):
+            lines = batch["lines"][off[b]:off[b + 1]].copy()
+            np.testing.assert_array_equal(sph[b], so.sphere_line_plot(lines, 500, alpha=0.1))
+        again = p(batch["segments"], batch["offsets"], want_sphere=True)[2]       # cached tables, no per-call host work
+        np.testing.assert_array_equal(again, sph)
+    finally:
+        p.ctx.close()

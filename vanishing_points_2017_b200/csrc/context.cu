@@ -78,7 +78,7 @@ int vpk_destroy(vpk_ctx* ctx) {
     for (auto& pe : ctx->pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (auto ev : ctx->event_pool) cudaEventDestroy(ev);
     ctx->d_lines.release(); ctx->d_segments.release(); ctx->d_offsets.release(); ctx->d_work.release();
-    ctx->d_hist.release(); ctx->d_img.release(); ctx->d_weights.release(); ctx->d_misc.release();
+    ctx->d_hist.release(); ctx->d_img.release(); ctx->d_weights.release(); ctx->d_misc.release(); ctx->d_curves_tab.release();
     ctx->h_stage.release();
     for (auto& e : ctx->marks) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);

@@ -475,11 +475,14 @@ int sphere_map_dev(vpk_ctx* ctx, const double* d_lines, const int32_t* d_offsets
         return VPK_OK;
     }
     if (mode == VPK_SPHERE_CURVES) {
-        // column -> first sample index table, exactly as numpy.linspace + the bin map
-        VPK_TRY(ctx->h_stage.ensure((S + 1) * sizeof(int32_t) + kLutMax + 1));
-        int32_t* first = ctx->h_stage.as<int32_t>();
-        uint8_t* lut = reinterpret_cast<uint8_t*>(first + S + 1);
-        {
+        // column -> first sample index table (exactly as numpy.linspace + the bin map) and the coverage LUT: built once per
+        // (S, alpha) and kept on the device, so a call needs no host work and no synchronisation
+        const size_t tab_bytes = (S + 1) * sizeof(int32_t) + kLutMax + 1;
+        if (ctx->curves_tab_S != S || ctx->curves_tab_alpha != alpha || !ctx->d_curves_tab.p) {
+            VPK_TRY(ctx->h_stage.ensure(tab_bytes));
+            VPK_TRY(ctx->d_curves_tab.ensure(tab_bytes));
+            int32_t* first = ctx->h_stage.as<int32_t>();
+            uint8_t* lut = reinterpret_cast<uint8_t*>(first + S + 1);
             const double start = -0.5 * kPi, stop = 0.5 * kPi;
             volatile double step = (stop - start) / (double)(kNumSamples - 1);
             int c = 0;
@@ -494,14 +497,14 @@ int sphere_map_dev(vpk_ctx* ctx, const double* d_lines, const int32_t* d_offsets
             while (c < S) first[++c] = kNumSamples;
             for (int k = 0; k <= kLutMax; ++k)
                 lut[k] = (uint8_t)floor(255.0 * (1.0 - pow(1.0 - alpha, (double)k)));
+            VPK_CUDA(cudaMemcpyAsync(ctx->d_curves_tab.p, first, tab_bytes, cudaMemcpyHostToDevice, ctx->stream));
+            VPK_CUDA(cudaStreamSynchronize(ctx->stream));          // once: the pinned staging buffer is reused by other calls
+            ctx->curves_tab_S = S; ctx->curves_tab_alpha = alpha;
         }
-        size_t tab_bytes = (S + 1) * sizeof(int32_t) + kLutMax + 1;
         size_t diff_bytes = sizeof(int32_t) * (size_t)(S + 1) * S * B;
-        VPK_TRY(ctx->d_work.ensure(tab_bytes));
         VPK_TRY(ctx->d_misc.ensure(diff_bytes));
-        VPK_CUDA(cudaMemcpyAsync(ctx->d_work.p, first, tab_bytes, cudaMemcpyHostToDevice, ctx->stream));
         VPK_CUDA(cudaMemsetAsync(ctx->d_misc.p, 0, diff_bytes, ctx->stream));
-        const int32_t* d_first = ctx->d_work.as<int32_t>();
+        const int32_t* d_first = ctx->d_curves_tab.as<int32_t>();
         const uint8_t* d_lut = reinterpret_cast<const uint8_t*>(d_first + S + 1);
         if (sumN > 0) {
             KernelScope ks(ctx, "sphere_curves");
@@ -517,7 +520,6 @@ int sphere_map_dev(vpk_ctx* ctx, const double* d_lines, const int32_t* d_offsets
                                                                                     d_hist, d_img);
             VPK_TRY(check_launch("curves_scan"));
         }
-        VPK_CUDA(cudaStreamSynchronize(ctx->stream));
         return VPK_OK;
     }
     set_error("sphere_map: unknown mode %d", mode);

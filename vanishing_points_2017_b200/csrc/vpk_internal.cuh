@@ -102,6 +102,9 @@ struct vpk_ctx {
 
     // generic workspaces (stage-private buffers live in the stage states)
     vpk::DBuf d_lines, d_segments, d_offsets, d_work, d_hist, d_img, d_weights, d_misc;
+    vpk::DBuf d_curves_tab;                 // curves mode: column -> first sample table + coverage LUT for (curves_tab_S, curves_tab_alpha)
+    int curves_tab_S = 0;
+    double curves_tab_alpha = -1.0;
     vpk::HBuf h_stage;
 
     cudaEvent_t marks[4] = {nullptr, nullptr, nullptr, nullptr};   // vpk_mark: device timestamps on this context's stream
