@@ -413,6 +413,111 @@ __global__ void sphere_curves_kernel(const double* __restrict__ lines, const int
     }
 }
 
+// ---- band form (S <= kBandMaxS): no difference array in HBM ----------------------------------------
+// sin / cos of the first sample of every column (entry S: the last sample), computed once per S with
+// the same device sincos as sample_row, so the rows below are those of sample_row bit for bit.
+__global__ void curves_trig_kernel(const int32_t* __restrict__ first, int S, double2* __restrict__ trig) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > S) return;
+    const double step = __ddiv_rn(kPi, (double)(kNumSamples - 1));
+    double sa, ca;
+    sincos(sample_alpha(min(first[c], kNumSamples - 1), step), &sa, &ca);
+    trig[c] = make_double2(sa, ca);
+}
+
+__device__ __forceinline__ int trig_row(double2 sc, double l0, double l1, double l2, double half_over_s, double s, int S) {
+    const double g = __ddiv_rn(__dsub_rn(__dmul_rn(-l0, sc.x), __dmul_rn(l2, sc.y)), l1);
+    const double beta = atan(g);
+    if (isnan(beta)) return -1;
+    return (S - 1) - angle_bin(beta, half_over_s, s);
+}
+
+// One CTA per (band of kBand columns, image); two threads take a line (16 columns each) and walk their
+// columns starting at column (lane / 2 mod 16), so that the lanes of a warp are in different columns =
+// different shared-memory banks at any time.  The row of the sample on a column border is evaluated
+// once and used by both neighbours.  Intervals go into a (S+1) x kBand difference array in shared
+// memory; the column-wise running sum and the coverage LUT follow in the same kernel.
+constexpr int kBand = 32;
+constexpr int kBandThreads = 256;
+constexpr int kBandSplit = 2;                    // threads per line
+constexpr int kBandPart = kBand / kBandSplit;    // columns per thread
+constexpr int kBandMaxS = 1536;                  // (S + 1) * kBand * 4 bytes of shared memory
+__global__ void __launch_bounds__(kBandThreads) sphere_curves_band_kernel(
+    const double* __restrict__ lines, const int32_t* __restrict__ offsets, int S, const int32_t* __restrict__ first,
+    const double2* __restrict__ trig, double f, const uint8_t* __restrict__ lut, uint32_t* __restrict__ counts,
+    uint8_t* __restrict__ img, int b0) {
+    extern __shared__ __align__(16) int32_t band_diff[];            // (S + 1) * kBand, then the segment sums
+    __shared__ int s_first[kBand + 1];
+    __shared__ double2 s_trig[kBand + 1];
+    const int b = b0 + blockIdx.y, c0 = blockIdx.x * kBand, nc = min(kBand, S - c0);
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int e = tid; e < (S + 1) * kBand; e += kBandThreads) band_diff[e] = 0;
+    if (tid <= nc) { s_first[tid] = first[c0 + tid]; s_trig[tid] = trig[c0 + tid]; }
+    __syncthreads();
+    const double s = (double)S;
+    const double half_over_s = __ddiv_rn(0.5, s);
+    const double step = __ddiv_rn(kPi, (double)(kNumSamples - 1));
+    const int n0 = offsets[b], n1 = offsets[b + 1];
+    const int p0 = (tid % kBandSplit) * kBandPart, np = min(kBandPart, nc - p0);      // this thread's columns p0 .. p0 + np
+    for (int line = n0 + tid / kBandSplit; np > 0 && line < n1; line += kBandThreads / kBandSplit) {
+        const double l0 = __dmul_rn(lines[3 * (int64_t)line + 0], f);      // sphere_mapping.py:55-56
+        const double l1 = __dmul_rn(lines[3 * (int64_t)line + 1], f);
+        const double l2 = lines[3 * (int64_t)line + 2];
+        const double astar = atan(l0 / l2);
+        const int kstar = isnan(astar) ? -10 : (int)floor((astar + 0.5 * kPi) / step);
+        int j = p0 + (lane / kBandSplit) % np;
+        int row_lo = trig_row(s_trig[j], l0, l1, l2, half_over_s, s, S);
+        for (int it = 0; it < np; ++it) {
+            const int row_hi = trig_row(s_trig[j + 1], l0, l1, l2, half_over_s, s, S);
+            const int k0 = s_first[j], kn = s_first[j + 1];
+            if (kn > k0) {
+                const int k1 = min(kn, kNumSamples - 1);
+                int rmin = S, rmax = -1;
+                if (row_lo >= 0) { rmin = row_lo; rmax = row_lo; }
+                if (row_hi >= 0) { rmin = min(rmin, row_hi); rmax = max(rmax, row_hi); }
+#pragma unroll
+                for (int e = -1; e <= 2; ++e) {
+                    const int k = kstar + e;
+                    if (k > k0 && k < k1) {
+                        const int r = sample_row(k, step, l0, l1, l2, half_over_s, s, S);
+                        if (r >= 0) { rmin = min(rmin, r); rmax = max(rmax, r); }
+                    }
+                }
+                if (rmax >= rmin) {
+                    atomicAdd(&band_diff[rmin * kBand + j], 1);
+                    atomicAdd(&band_diff[(rmax + 1) * kBand + j], -1);
+                }
+            }
+            if (++j == p0 + np) {
+                j = p0;
+                if (it + 1 < np) row_lo = trig_row(s_trig[p0], l0, l1, l2, half_over_s, s, S);
+            } else {
+                row_lo = row_hi;
+            }
+        }
+    }
+    __syncthreads();
+    // running sum down the columns: thread (seg, j) owns rows [seg*rows_per, ...) of column j
+    constexpr int kSegs = kBandThreads / kBand;
+    const int seg = tid / kBand, jc = tid % kBand;
+    const int rows_per = (S + kSegs - 1) / kSegs;
+    const int r0 = seg * rows_per, r1 = min(S, r0 + rows_per);
+    int32_t* seg_sum = band_diff + (S + 1) * kBand;                  // kSegs * kBand
+    int tot = 0;
+    for (int r = r0; r < r1; ++r) tot += band_diff[r * kBand + jc];
+    seg_sum[seg * kBand + jc] = tot;
+    __syncthreads();
+    if (jc >= nc) return;
+    int run = 0;
+    for (int q = 0; q < seg; ++q) run += seg_sum[q * kBand + jc];
+    for (int r = r0; r < r1; ++r) {
+        run += band_diff[r * kBand + jc];
+        const int64_t o = ((int64_t)b * S + r) * S + c0 + jc;
+        if (counts) counts[o] = (uint32_t)run;
+        if (img) img[o] = lut[min(run, kLutMax)];
+    }
+}
+
 // column-wise running sum of the difference array -> counts, LUT -> uint8
 __global__ void curves_scan_kernel(const int32_t* __restrict__ diff, int B, int S, const uint8_t* __restrict__ lut,
                                    uint32_t* __restrict__ counts, uint8_t* __restrict__ img) {
@@ -478,9 +583,10 @@ int sphere_map_dev(vpk_ctx* ctx, const double* d_lines, const int32_t* d_offsets
         // column -> first sample index table (exactly as numpy.linspace + the bin map) and the coverage LUT: built once per
         // (S, alpha) and kept on the device, so a call needs no host work and no synchronisation
         const size_t tab_bytes = (S + 1) * sizeof(int32_t) + kLutMax + 1;
+        const size_t trig_off = (tab_bytes + 15) / 16 * 16;             // then sin / cos of the column borders (band form)
         if (ctx->curves_tab_S != S || ctx->curves_tab_alpha != alpha || !ctx->d_curves_tab.p) {
             VPK_TRY(ctx->h_stage.ensure(tab_bytes));
-            VPK_TRY(ctx->d_curves_tab.ensure(tab_bytes));
+            VPK_TRY(ctx->d_curves_tab.ensure(trig_off + (S + 1) * sizeof(double2)));
             int32_t* first = ctx->h_stage.as<int32_t>();
             uint8_t* lut = reinterpret_cast<uint8_t*>(first + S + 1);
             const double start = -0.5 * kPi, stop = 0.5 * kPi;
@@ -498,14 +604,34 @@ int sphere_map_dev(vpk_ctx* ctx, const double* d_lines, const int32_t* d_offsets
             for (int k = 0; k <= kLutMax; ++k)
                 lut[k] = (uint8_t)floor(255.0 * (1.0 - pow(1.0 - alpha, (double)k)));
             VPK_CUDA(cudaMemcpyAsync(ctx->d_curves_tab.p, first, tab_bytes, cudaMemcpyHostToDevice, ctx->stream));
+            curves_trig_kernel<<<(unsigned)(S / 128 + 1), 128, 0, ctx->stream>>>(
+                ctx->d_curves_tab.as<int32_t>(), S, reinterpret_cast<double2*>(static_cast<char*>(ctx->d_curves_tab.p) + trig_off));
+            VPK_TRY(check_launch("curves_trig"));
             VPK_CUDA(cudaStreamSynchronize(ctx->stream));          // once: the pinned staging buffer is reused by other calls
             ctx->curves_tab_S = S; ctx->curves_tab_alpha = alpha;
         }
+        const int32_t* d_first = ctx->d_curves_tab.as<int32_t>();
+        const uint8_t* d_lut = reinterpret_cast<const uint8_t*>(d_first + S + 1);
+        if (S <= kBandMaxS && !getenv("VPK_CURVES_GLOBAL_DIFF")) {
+            const size_t smem = sizeof(int32_t) * ((size_t)(S + 1) * kBand + kBandThreads);
+            if (smem > ctx->curves_band_smem) {
+                VPK_CUDA(cudaFuncSetAttribute(sphere_curves_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ctx->curves_band_smem = smem;
+            }
+            for (int b0 = 0; b0 < B; b0 += 65535) {
+                KernelScope ks(ctx, "sphere_curves");
+                dim3 grid((unsigned)((S + kBand - 1) / kBand), (unsigned)std::min(B - b0, 65535));
+                sphere_curves_band_kernel<<<grid, kBandThreads, smem, ctx->stream>>>(
+                    d_lines, d_offsets, S, d_first, reinterpret_cast<const double2*>(reinterpret_cast<const char*>(d_first) + trig_off),
+                    1.0, d_lut, d_hist, d_img, b0);
+                VPK_TRY(check_launch("sphere_curves"));
+            }
+            return VPK_OK;
+        }
+        // very large grids: difference array in HBM, one CTA per line, separate scan
         size_t diff_bytes = sizeof(int32_t) * (size_t)(S + 1) * S * B;
         VPK_TRY(ctx->d_misc.ensure(diff_bytes));
         VPK_CUDA(cudaMemsetAsync(ctx->d_misc.p, 0, diff_bytes, ctx->stream));
-        const int32_t* d_first = ctx->d_curves_tab.as<int32_t>();
-        const uint8_t* d_lut = reinterpret_cast<const uint8_t*>(d_first + S + 1);
         if (sumN > 0) {
             KernelScope ks(ctx, "sphere_curves");
             int threads = S >= 512 ? 512 : ((S + 31) / 32) * 32;

@@ -105,6 +105,7 @@ struct vpk_ctx {
     vpk::DBuf d_curves_tab;                 // curves mode: column -> first sample table + coverage LUT for (curves_tab_S, curves_tab_alpha)
     int curves_tab_S = 0;
     double curves_tab_alpha = -1.0;
+    size_t curves_band_smem = 0;            // dynamic shared memory the band kernel is opted in for on this device
     vpk::HBuf h_stage;
 
     cudaEvent_t marks[4] = {nullptr, nullptr, nullptr, nullptr};   // vpk_mark: device timestamps on this context's stream
