@@ -71,3 +71,58 @@ def test_fast_path_never_disagrees_with_float64_cells():
     ok, frow, fcol = fast(L[ii], L[jj], 500)
     assert not np.any(ok & (~valid | (frow != row) | (fcol != col)))
     assert accepted > 0.85 * total          # the fast path must carry the bulk of the pairs
+
+
+# ---- curves mode: csrc/sphere.cu::fast_row ---------------------------------------------------------------------
+U = f32(2.0 ** -24)
+
+
+def exact_rows(L, sa, ca, S):
+    """sphere_mapping.py:61-63 + coordinate_conversion.py:29-30 in float64 (what trig_row computes)."""
+    with np.errstate(all="ignore"):
+        beta = np.arctan((-L[:, 0:1] * sa[None] - L[:, 2:3] * ca[None]) / L[:, 1:2])
+        r = np.clip(np.floor(((beta / np.pi + 0.5) - 0.5 / S) * S + 0.5), 0, S - 1)
+    return np.where(np.isnan(beta), -1, (S - 1) - r).astype(np.int64)
+
+
+def fast_rows(L, sa, ca, S):
+    with np.errstate(all="ignore"):
+        l0 = L[:, 0:1].astype(f32); l1 = L[:, 1:2].astype(f32); l2 = L[:, 2:3].astype(f32)
+        inv = ulp_noise((f32(1) / l1).astype(f32), 1)
+        p = (-l0) * sa.astype(f32)[None]
+        q = l2 * ca.astype(f32)[None]
+        g = (p - q) * inv
+        eg = f32(10) * U * ((np.abs(p) + np.abs(q)) * np.abs(inv))
+        gm = np.maximum(np.abs(g) - eg, f32(0))
+        dbeta = eg / (f32(1) + gm * gm) + f32(2.0 ** -22)
+        beta = ulp_noise(np.arctan(g).astype(f32), 2)
+        sop = f32(S / np.pi); hs = f32(0.5 * S)
+        u = (beta.astype(np.float64) * np.float64(sop) + np.float64(hs)).astype(f32)       # fmaf: one rounding
+        m = f32(2) * (dbeta * sop + f32(2.0 ** -23) * f32(S)) + f32(1e-6)
+        fl = np.floor(u)
+        ok = (u - fl > m) & (f32(1) - (u - fl) > m) & (np.abs(u) < f32(1e9))
+        r = np.clip(np.where(ok, fl, 0).astype(np.int64), 0, S - 1)
+    return ok, (S - 1) - r
+
+
+def test_curves_fast_path_never_disagrees_with_float64_rows():
+    """tools/check_fast_row.py runs the same check over 137 M (line, sample) pairs."""
+    k = np.unique(np.concatenate([np.arange(0, 10000, 23), [9999]]))
+    alpha = k * (np.pi / 9999) + (-0.5 * np.pi)
+    alpha[-1] = 0.5 * np.pi
+    sa, ca = np.sin(alpha), np.cos(alpha)
+    total = accepted = 0
+    for seed, n, S in ((701, 800, 500), (702, 500, 250), (703, 300, 1536)):
+        L = synth.make_scene(seed, n, 800, 600, noise_deg=0.5)["lines"]
+        ok, fr = fast_rows(L, sa, ca, S)
+        assert not np.any(ok & (fr != exact_rows(L, sa, ca, S)))
+        total += ok.size; accepted += int(ok.sum())
+    assert accepted > 0.99 * total
+    n = 1200
+    L = rs.standard_normal((n, 3)) * np.exp(rs.uniform(-8, 8, (n, 3)))
+    L[: n // 4, 1] *= 1e-7                       # |g| huge
+    L[n // 4: n // 2, 1] *= 1e7                  # g ~ 0
+    L[n // 2: 5 * n // 8, 1] = 0.0               # division by zero
+    L[5 * n // 8: 3 * n // 4, 0] = 0.0
+    ok, fr = fast_rows(L, sa, ca, 500)
+    assert not np.any(ok & (fr != exact_rows(L, sa, ca, 500)))

@@ -69,6 +69,34 @@ def test_curves_counts_bit_exact(sm, N, S):
     np.testing.assert_array_equal(r["image"][0], so.curve_image(ref, 0.1))
 
 
+def test_curves_kernel_variants_are_bit_identical(sm, monkeypatch):
+    """The band kernel with float32 pre-binned rows (default), the same kernel in float64 only, and the
+    one-CTA-per-line kernel with its difference array in HBM (grids beyond 1536 cells) give the same counts,
+    on a ragged batch with an empty image and on lines of wild scales / zero components."""
+    rs = np.random.RandomState(3)
+    ns = [0, 700, 33, 1, 260]
+    off = np.concatenate([[0], np.cumsum(ns)]).astype(np.int32)
+    lines = np.concatenate([synth.make_scene(900 + i, max(n, 1))["lines"][:n] for i, n in enumerate(ns)])
+    wild = rs.standard_normal((260, 3)) * np.exp(rs.uniform(-8, 8, (260, 3)))
+    wild[:20, 1] = 0.0
+    wild[20:40, 0] = 0.0
+    wild[40:60, 2] = 0.0
+    lines[-260:] = wild
+    for S in (500, 77):
+        base = sm.sphere_map_batch(lines, off, S, "curves")
+        for var in ("VPK_CURVES_F64", "VPK_CURVES_GLOBAL_DIFF"):
+            monkeypatch.setenv(var, "1")
+            other = sm.sphere_map_batch(lines, off, S, "curves")
+            monkeypatch.delenv(var)
+            np.testing.assert_array_equal(base["hist"], other["hist"])
+            np.testing.assert_array_equal(base["image"], other["image"])
+        assert base["hist"][0].sum() == 0
+        ref = so.sphere_curve_counts(lines[off[1]:off[2]], S)
+        np.testing.assert_array_equal(base["hist"][1].astype(np.int64), ref)
+    big = sm.sphere_map_batch(lines[off[1]:off[2]], [0, 700], 1600, "curves")          # > kBandMaxS: the HBM form
+    np.testing.assert_array_equal(big["hist"][0].astype(np.int64), so.sphere_curve_counts(lines[off[1]:off[2]], 1600))
+
+
 def test_sphere_line_plot_drop_in(sm):
     sc = synth.make_scene(77, 150)
     lines = sc["lines"].copy()
