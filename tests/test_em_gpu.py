@@ -56,7 +56,8 @@ def test_against_reference_golden(em, path):
 
 
 @pytest.mark.parametrize("seed,N,noise", [(1, 3, 0.5), (2, 12, 0.5), (3, 64, 0.5), (4, 333, 1.0), (5, 1000, 0.5),
-                                          (6, 520, 2.5)])
+                                          (6, 520, 2.5), (7, 1, 0.5), (8, 5, 0.5), (9, 9, 0.5), (10, 33, 0.5),
+                                          (11, 129, 0.5)])
 def test_against_oracle(em, seed, N, noise):
     sc = synth.make_scene(7000 + seed, N, 800, 600, noise_deg=noise)
     img = so.votes_to_image(so.sphere_votes(sc["lines"], 500))

@@ -44,13 +44,14 @@ def compare(res, ref):
 
 
 # N just above the slab-split thresholds of the weight-matrix kernel (1536, 3072), ECD's and the stress
-# sweep's maxima, with the default 25 and the stress config's 32 initial hypotheses
+# sweep's maxima and beyond, with the default 25 and the stress config's 32 initial hypotheses
 @pytest.mark.parametrize("seed,N,noise,kw", [
     (11, 1537, 1.0, {}),
     (12, 2200, 1.0, dict(num_init_vp=32)),
     (13, 3100, 1.0, {}),
     (14, 5000, 1.0, dict(num_init_vp=32)),
-], ids=["n1537", "n2200_m32", "n3100", "n5000_m32"])
+    (15, 6000, 1.0, {}),                      # beyond every configuration of BASELINE.json: there is no cap on N
+], ids=["n1537", "n2200_m32", "n3100", "n5000_m32", "n6000"])
 def test_large_images_against_oracle(em, seed, N, noise, kw):
     sc, img, resp = scene(7100 + seed, N, noise)
     ref = vo.expectation_maximisation(sc["lines"].copy(), sc["segments"].copy(), resp.copy(), sphere_image=img, **kw)

@@ -615,6 +615,10 @@ __global__ void __launch_bounds__(kPostThreads, 2) em_post_kernel(EmParams P, Ti
         if (P.stats && T.tid == 0) {
             for (int k = 0; k < 10; ++k) atomicAdd(P.stats + 8 + k, (unsigned long long)sc.mark[k]);
             atomicAdd(P.stats + 18, 1ull);
+            if (sc.mark[15] > 0) {                              // split_best_vp ran to its end: marks 11..15 of the split
+                for (int k = 11; k < 16; ++k) atomicAdd(P.stats + 8 + k, (unsigned long long)sc.mark[k]);
+                atomicAdd(P.stats + 24, 1ull);
+            }
         }
 #endif
     }
@@ -1410,6 +1414,14 @@ static int wave_run(vpk_ctx* ctx, EmState* st) {
         fprintf(stderr, "[vpk_em] POST cycles per slot-superstep (%llu):", mk[10]);
         for (int k = 0; k < 10; ++k) fprintf(stderr, " m%d=%.0f", k, (double)mk[k] / (double)std::max<unsigned long long>(mk[10], 1));
         fprintf(stderr, "\n");
+        if (W.mode != MODE_FUSED) {
+            unsigned long long sp[6];
+            VPK_CUDA(cudaMemcpy(sp, W.P.stats + 19, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[vpk_em] split cycles per completed split (%llu): stats=%.0f pick=%.0f distances=%.0f linkage=%.0f refit=%.0f\n", sp[5],
+                    (double)sp[0] / std::max<unsigned long long>(sp[5], 1), (double)sp[1] / std::max<unsigned long long>(sp[5], 1),
+                    (double)sp[2] / std::max<unsigned long long>(sp[5], 1), (double)sp[3] / std::max<unsigned long long>(sp[5], 1),
+                    (double)sp[4] / std::max<unsigned long long>(sp[5], 1));
+        }
 #endif
     }
     return VPK_OK;

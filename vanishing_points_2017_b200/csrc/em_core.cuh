@@ -1183,6 +1183,7 @@ VPK_DEVFN void average_linkage_two(double* D, int n, int* rep, int* mate, double
 VPK_DEVFN int split_best_vp(const Img& im, EmSlot& st, PostScratch& sc, double min_diff, double* big, size_t big_cap,
                             int* big_lock, const Team& T) {
     const int M = st.M, N = im.N, tid = T.tid;
+    VPK_MARK(sc, T, 10);
     argmax_assoc(im, M, T);
     // global maximum of w (weightMatrix.max(), :539) only decides the sign of the greedy entries
     double lm = -INFINITY;
@@ -1216,6 +1217,7 @@ VPK_DEVFN int split_best_vp(const Img& im, EmSlot& st, PostScratch& sc, double m
         if (T.lane == 0) { sc.ang[m] = c > 0 ? sqrt(var / c) : nan(""); st.cnt[m] = call; }
     }
     team_sync();
+    VPK_MARK(sc, T, 11);
     if (tid == 0) {
         // argsort(std)[::-1]: ascending, NaN last, stable; then reversed (:546-547)
         int ord[kMaxM];
@@ -1245,6 +1247,7 @@ VPK_DEVFN int split_best_vp(const Img& im, EmSlot& st, PostScratch& sc, double m
     }
     team_sync();
     const int worst = sc.ia;
+    VPK_MARK(sc, T, 12);
     if (worst < 0) return -1;
     const int nw = st.cnt[worst];
     // scratch layout (doubles): D[nw*nw] | csize nnd height [nw each] | ints: idx rep mate nn act [nw each] keep [nw/2]
@@ -1298,7 +1301,9 @@ VPK_DEVFN int split_best_vp(const Img& im, EmSlot& st, PostScratch& sc, double m
         D[e] = d;
     }
     team_sync();
+    VPK_MARK(sc, T, 13);
     average_linkage_two(D, nw, rep, mate, csize, nnd, nn, act, height, keep, sc, T);
+    VPK_MARK(sc, T, 14);
     // per cluster: smallest right-singular vector of the lweight-scaled lines (:580-602)
     for (int c = T.warp; c < 2; c += T.nwarps) {
         double g[6] = {0, 0, 0, 0, 0, 0};
@@ -1346,6 +1351,7 @@ VPK_DEVFN int split_best_vp(const Img& im, EmSlot& st, PostScratch& sc, double m
         }
     }
     team_sync();
+    VPK_MARK(sc, T, 15);
     return sc.flag != 0 ? 1 : 0;
 }
 
