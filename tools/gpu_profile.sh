@@ -13,7 +13,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:"em_(estep|wmat|post)_kernel" -s 30 -c 9 \
     -o gpurun_out/${TAG}_em_steps -f python tools/run_once.py --runs 1 > gpurun_out/${TAG}_em_steps.log 2>&1
 # full capture: the once-per-batch kernels
-ncu --set full --clock-control none --import-source on -k regex:"em_pair|em_init|sphere_votes|sphere_items|gemm_bf16|splitk|lrn_pool|votes_image|plane_max|conv1_operand" -c 20 \
+ncu --set full --clock-control none --import-source on -k regex:"em_pair|em_init|sphere_votes|sphere_items|sphere_curves|gemm_bf16|splitk|lrn_pool|votes_image|plane_max|conv1_operand" -c 20 \
     -o gpurun_out/${TAG}_once -f python tools/run_once.py --runs 1 > gpurun_out/${TAG}_once.log 2>&1
 ls -la gpurun_out | tail -8
 # summarise on the box and drop the reports (gpurun_out/ may carry at most 64 MiB back)
