@@ -618,6 +618,12 @@ __global__ void __launch_bounds__(kPostThreads, 2) em_post_kernel(EmParams P, Ti
             if (sc.mark[15] > 0) {                              // split_best_vp ran to its end: marks 11..15 of the split
                 for (int k = 11; k < 16; ++k) atomicAdd(P.stats + 8 + k, (unsigned long long)sc.mark[k]);
                 atomicAdd(P.stats + 24, 1ull);
+                unsigned long long tot = 0;
+                for (int k = 11; k < 16; ++k) tot += (unsigned long long)sc.mark[k];
+                if (atomicMax(P.stats + 25, tot) < tot) {        // phases of the slowest split (diagnostic; not race-free)
+                    for (int k = 11; k < 16; ++k) P.stats[15 + k] = (unsigned long long)sc.mark[k];
+                    P.stats[31] = (unsigned long long)st.N;
+                }
             }
         }
 #endif
@@ -1421,6 +1427,10 @@ static int wave_run(vpk_ctx* ctx, EmState* st) {
                     (double)sp[0] / std::max<unsigned long long>(sp[5], 1), (double)sp[1] / std::max<unsigned long long>(sp[5], 1),
                     (double)sp[2] / std::max<unsigned long long>(sp[5], 1), (double)sp[3] / std::max<unsigned long long>(sp[5], 1),
                     (double)sp[4] / std::max<unsigned long long>(sp[5], 1));
+            unsigned long long mx[7];
+            VPK_CUDA(cudaMemcpy(mx, W.P.stats + 25, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[vpk_em] slowest split (N = %llu): %llu cycles: stats=%llu pick=%llu distances=%llu linkage=%llu refit=%llu\n", mx[6], mx[0],
+                    mx[1], mx[2], mx[3], mx[4], mx[5]);
         }
 #endif
     }

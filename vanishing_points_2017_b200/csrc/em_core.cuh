@@ -1063,31 +1063,32 @@ VPK_DEVFN void compact_vps(EmSlot& st, const int* rem, const Team& T) {
 // index), which keeps the globally closest pair reciprocal (progress).
 // Labels follow _hc_cut: label 0 = the root's child with the larger node id,
 // i.e. the one formed later = with the larger merge height (a leaf: its index).
+// have_nn: nn / nnd of the first round are already filled in (the caller found them while writing D).
 VPK_DEVFN void average_linkage_two(double* D, int n, int* rep, int* mate, double* csize, double* nnd, int* nn,
-                                    int* act, double* height, int* keep, PostScratch& sc, const Team& T) {
+                                    int* act, double* height, int* keep, PostScratch& sc, const Team& T, bool have_nn = false) {
     const int tid = T.tid, NT = T.nthreads;
     for (int i = tid; i < n; i += NT) { rep[i] = i; csize[i] = 1.0; height[i] = -INFINITY; act[i] = i; }
     team_sync();
     int nact = n;
     while (nact > 2) {
-        // 1. nearest neighbour of every active cluster, one warp per row.  act is ascending, so the
-        //    first minimum along a row is the tie-break by index.
-        for (int f = T.warp; f < nact; f += T.nwarps) {
+        // 1. nearest neighbour of every active cluster, one warp per row, eight loads per lane in flight (the
+        //    matrix lives in the L2).  act is ascending, so the first minimum along a row is the tie-break by index.
+        for (int f = T.warp; f < nact && !have_nn; f += T.nwarps) {
             const int a = act[f];
             const double* row = D + (size_t)a * n;
             double bd = INFINITY;
             int bb = -1;
-            for (int g0 = T.lane; g0 < nact; g0 += 4 * T.lanes) {
-                double v[4];
-                int b[4];
+            for (int g0 = T.lane; g0 < nact; g0 += 8 * T.lanes) {
+                double v[8];
+                int b[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     const int g = g0 + u * T.lanes;
                     b[u] = g < nact ? act[g] : a;
                     v[u] = b[u] != a ? row[b[u]] : INFINITY;
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     if (b[u] == a) continue;
                     const double x = isnan(v[u]) ? INFINITY : v[u];
                     if (bb < 0 || x < bd) { bd = x; bb = b[u]; }
@@ -1096,6 +1097,7 @@ VPK_DEVFN void average_linkage_two(double* D, int n, int* rep, int* mate, double
             warp_min_pair(bd, bb);
             if (T.lane == 0) { nn[a] = bb; nnd[a] = bd; }
         }
+        have_nn = false;
         team_sync();
         // 2. reciprocal pairs; the smaller index of a pair keeps the merged cluster (ordered list `keep`)
         if (T.warp == 0) {
@@ -1120,24 +1122,43 @@ VPK_DEVFN void average_linkage_two(double* D, int n, int* rep, int* mate, double
         }
         team_sync();
         const int k = sc.l_nflag;
-        // 3. distances of the merged clusters to every surviving cluster.  Each new entry depends on
-        //    old entries that no other thread of this round writes.
-        for (int e = tid; e < k * nact; e += NT) {
-            const int X = keep[e / nact], Y = act[e % nact];
-            const int my = mate[Y];
-            if (Y == X || (my >= 0 && my < Y)) continue;         // itself / Y is absorbed this round
-            const bool ymerged = my > Y;
-            if (ymerged && Y < X) continue;                      // pair of merged clusters: done by (Y, X)
-            const int b = mate[X];
+        // 3. distances of the merged clusters to every surviving cluster: one warp per merged cluster, four columns
+        //    per lane in flight.  Each new entry depends on old entries that no other thread of this round writes.
+        for (int q = T.warp; q < k; q += T.nwarps) {
+            const int X = keep[q], b = mate[X];
             const double na = csize[X], nb = csize[b];
-            double v = (na * D[(size_t)X * n + Y] + nb * D[(size_t)b * n + Y]) / (na + nb);     // average_merge
-            if (ymerged) {
-                const double v2 = (na * D[(size_t)X * n + my] + nb * D[(size_t)b * n + my]) / (na + nb);
-                const double nc = csize[Y], nd = csize[my];
-                v = (nc * v + nd * v2) / (nc + nd);
+            double* rx = D + (size_t)X * n;
+            const double* rb = D + (size_t)b * n;
+            for (int f0 = T.lane; f0 < nact; f0 += 4 * T.lanes) {
+                int Y[4], my[4];
+                bool go[4];
+                double x1[4], x2[4], y1[4], y2[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int f = f0 + u * T.lanes;
+                    Y[u] = f < nact ? act[f] : X;
+                    my[u] = mate[Y[u]];
+                    // skipped: itself / Y is absorbed this round / pair of merged clusters, done by (Y, X)
+                    go[u] = !(Y[u] == X || (my[u] >= 0 && my[u] < Y[u]) || (my[u] > Y[u] && Y[u] < X));
+                    x1[u] = x2[u] = y1[u] = y2[u] = 0.0;
+                    if (go[u]) {
+                        x1[u] = rx[Y[u]]; x2[u] = rb[Y[u]];
+                        if (my[u] > Y[u]) { y1[u] = rx[my[u]]; y2[u] = rb[my[u]]; }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (!go[u]) continue;
+                    double v = (na * x1[u] + nb * x2[u]) / (na + nb);                             // average_merge
+                    if (my[u] > Y[u]) {
+                        const double v2 = (na * y1[u] + nb * y2[u]) / (na + nb);
+                        const double nc = csize[Y[u]], nd = csize[my[u]];
+                        v = (nc * v + nd * v2) / (nc + nd);
+                    }
+                    rx[Y[u]] = v;
+                    D[(size_t)Y[u] * n + X] = v;
+                }
             }
-            D[(size_t)X * n + Y] = v;
-            D[(size_t)Y * n + X] = v;
         }
         team_sync();
         // 4. bookkeeping, then drop the absorbed clusters from the active list (order kept)
@@ -1294,15 +1315,46 @@ VPK_DEVFN int split_best_vp(const Img& im, EmSlot& st, PostScratch& sc, double m
         }
     }
     team_sync();
-    for (size_t e = tid; e < (size_t)nw * nw; e += T.nthreads) {
-        int a = (int)(e / nw), b = (int)(e % nw);
-        double d = 0.0;
-        if (a != b) d = 1.0 - cosangle(load_seg(im.lp, idx[a]), load_seg(im.lp, idx[b]), 2.0);     // :572
-        D[e] = d;
+    // Ldist = 1 - cosangle(f = 2) (:572), one warp per row.  Direction and length of every line are taken once (the
+    // expressions of cosangle(), so every entry has the bits of the per-pair evaluation); they sit in the three
+    // float64 arrays the clustering initialises later.  While a row is written its nearest neighbour is found, which
+    // is the first round of the clustering (kept in redv until the rows are done: nnd holds the directions).
+    static_assert(kLinkMax <= kPostThreads, "redv holds the first nearest-neighbour distances");
+    double* dir_x = nnd; double* dir_y = csize; double* dir_n = height;
+    for (int q = tid; q < nw; q += T.nthreads) {
+        const Seg sg = load_seg(im.lp, idx[q]);
+        const double vx = sg.x1 - sg.x2, vy = sg.y1 - sg.y2;
+        dir_x[q] = vx; dir_y[q] = vy; dir_n[q] = sqrt(vx * vx + vy * vy);
     }
     team_sync();
+    const bool fuse_nn = nw <= kLinkMax && nw > 2;
+    for (int a = T.warp; a < nw; a += T.nwarps) {
+        const double v1x = dir_x[a], v1y = dir_y[a], n1 = dir_n[a];
+        double* row = D + (size_t)a * nw;
+        double bd = INFINITY;
+        int bb = -1;
+        for (int b = T.lane; b < nw; b += T.lanes) {
+            double d = 0.0;
+            if (a != b) {
+                const double v2x = dir_x[b], v2y = dir_y[b];
+                const double c = fabs((v1x * v2x + v1y * v2y) / (n1 * dir_n[b]));
+                d = 1.0 - cos_clipped_multiple(c, 2.0);
+                const double x = isnan(d) ? INFINITY : d;
+                if (bb < 0 || x < bd) { bd = x; bb = b; }
+            }
+            row[b] = d;
+        }
+        if (fuse_nn) {
+            warp_min_pair(bd, bb);
+            if (T.lane == 0) { nn[a] = bb; sc.redv[a] = bd; }
+        }
+    }
+    team_sync();
+    if (fuse_nn)
+        for (int q = tid; q < nw; q += T.nthreads) nnd[q] = sc.redv[q];
+    team_sync();
     VPK_MARK(sc, T, 13);
-    average_linkage_two(D, nw, rep, mate, csize, nnd, nn, act, height, keep, sc, T);
+    average_linkage_two(D, nw, rep, mate, csize, nnd, nn, act, height, keep, sc, T, fuse_nn);
     VPK_MARK(sc, T, 14);
     // per cluster: smallest right-singular vector of the lweight-scaled lines (:580-602)
     for (int c = T.warp; c < 2; c += T.nwarps) {
