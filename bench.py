@@ -254,7 +254,7 @@ def run_reference(args, rank, world):
                                        "BLAS/torch threads = %d" % (sample, cores),
                              "reference_em": ref_em},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------ GPU arm
@@ -612,10 +612,21 @@ def run_ours(args, rank, world, local_rank):
                             "stream; the pair pass then does not overlap stages 1-2 as it does in the timed legs)",
             "images_with_vps": n_ok,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_RESULT_FD = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
@@ -641,6 +652,12 @@ def main():
     ap.add_argument("--settle", type=int, default=30, help="upper bound of the extra untimed settling steps after the warm-up")
     ap.add_argument("--clock-period", type=float, default=0.005, help="seconds between NVML clock samples in the timed region")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 (NCCL prints its
+    # version banner there) are sent to stderr; emit() writes the line to the real stdout
+    sys.stdout.flush()
+    global _RESULT_FD
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
