@@ -114,11 +114,22 @@ __device__ __forceinline__ bool em_mbar_try_wait(uint32_t bar, uint32_t parity) 
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps instead of hanging the GPU.
+// Bounded wait: a protocol bug traps instead of hanging the GPU (the host then reports the failing launch by name,
+// check_launch / KernelScope).  The bound is wall time on the device (20 s of %globaltimer once 2^24 polls have
+// failed), not a poll count alone, so a time-sliced or preempted context is not mistaken for one.  No printf: the
+// call costs the W kernel registers (measured 1.74 -> 1.765 ms per YUD batch).
+__device__ __forceinline__ unsigned long long em_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void em_mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t i = 0; i < (1u << 24); ++i)
         if (em_mbar_try_wait(bar, parity)) return;
-    __trap();
+    // not reached in a run that is neither broken nor descheduled for long: now bound the wait by time
+    const unsigned long long t0 = em_globaltimer();
+    while (!em_mbar_try_wait(bar, parity))
+        if (em_globaltimer() - t0 > 20000000000ull) __trap();
 }
 __device__ __forceinline__ void em_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

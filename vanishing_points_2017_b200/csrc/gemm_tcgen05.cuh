@@ -83,11 +83,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps instead of hanging the GPU.
+// Bounded wait: a protocol bug traps instead of hanging the GPU (the host then reports the failing launch by name,
+// check_launch / KernelScope).  The bound is wall time on the device (20 s of %globaltimer once 2^22 polls have
+// failed), not a poll count alone, so a time-sliced or preempted context is not mistaken for one.  No printf here: a call in
+// this kernel costs registers in the pipeline loops (measured: conv2 0.46 -> 0.51 ms).
+__device__ __forceinline__ unsigned long long mbar_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t i = 0; i < (1u << 22); ++i)
         if (mbar_try_wait(bar, parity)) return;
-    __trap();
+    // not reached in a run that is neither broken nor descheduled for long: now bound the wait by time
+    const unsigned long long t0 = mbar_globaltimer();
+    while (!mbar_try_wait(bar, parity))
+        if (mbar_globaltimer() - t0 > 20000000000ull) __trap();
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
