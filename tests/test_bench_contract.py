@@ -1,0 +1,39 @@
+"""bench.py's contract with the driver, as far as it can be checked without a GPU: the reference arm
+(`--impl reference`, the CPU path on the host cores) prints exactly ONE line on stdout, a JSON object with the
+keys the driver reads, and under torchrun only rank 0 prints (the missing-GPU behaviour of the product path is
+covered by tests/test_abi.py)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+
+
+def run_bench(*args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + list(args), capture_output=True, text=True,
+                          cwd=ROOT, env=e, timeout=600)
+
+
+def test_reference_arm_prints_one_json_line():
+    r = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0", "--images", "4", "--no-reference-em")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["metric"].startswith("images/sec") and d["unit"] == "images/s" and d["value"] > 0
+    assert d["steps"] == 1 and d["warmup"] == 0 and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_print_nothing():
+    r = run_bench("--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+                  env={"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip() == ""
