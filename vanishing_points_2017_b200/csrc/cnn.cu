@@ -24,6 +24,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct CnnState {
     bool loaded = false;
     bool attr2 = false, attr3 = false, attr4 = false;     // dynamic shared-memory opt-in of the two GEMM instantiations: per CONTEXT (device)
+    bool attr_p3 = false, attr_p4 = false, attr_p6 = false;      // ... of the persistent instantiations
+    bool persistent = true;                                  // conv3-5 through the persistent kernel (VPK_GEMM_PERSIST=0: off)
     EncodeTiledFn encode = nullptr;
     // bf16 weight matrices (K-major) and fp32 biases, one per layer conv1..fc8
     DBuf w[8], b[8], mean;
@@ -257,6 +259,27 @@ int launch_gemm(vpk_ctx* ctx, const GemmCall& c) {
     dim3 grid(m_tiles, n_tiles, (c.groups / fold) * ksplit);
     const size_t stage = kABytes + (size_t)c.p.bn * kBK * 2;
     KernelScope ks(ctx, c.name);
+    if (ksplit == 1 && st->persistent && !c.p.lrn) {
+        // persistent CTAs with two accumulators in tensor memory (gemm_tcgen05.cuh): two per SM when both accumulators of
+        // both fit the 512 columns, else one per SM with a deeper ring.  Measured on the YUD batch: conv3 0.219 -> 0.187,
+        // conv4 0.215 -> 0.168, conv5 0.124 -> 0.103 ms.  Not for the layers with the LRN in the epilogue: conv2 needs all
+        // 512 columns for two accumulators, i.e. one CTA = eight epilogue warps per SM, and its epilogue then
+        // limits it (0.458 -> 0.578 ms); conv1 (three K blocks per tile) is unchanged (0.261 / 0.264 ms).
+        int ncols1 = 32;
+        while (ncols1 < c.p.bn * fold) ncols1 <<= 1;
+        const int total = m_tiles * n_tiles * (c.groups / fold);
+        const int per_sm = 2 * ncols1 <= 256 ? 2 : 1;
+        const int ctas = std::min(total, per_sm * ctx->num_sms);
+        auto launch = [&](auto kern, int stages, int max_stage, bool& done) -> int {
+            const size_t smem = stages * stage + 1024;
+            if (!done) { VPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, stages * max_stage + 1024)); done = true; }
+            kern<<<ctas, kGemmThreads, smem, ctx->stream>>>(ma, mb, c.p, m_tiles, n_tiles, total);
+            return check_launch(c.name);
+        };
+        if (per_sm == 2) return launch(gemm_bf16_tcgen05_persistent_kernel<3>, 3, kABytes + 128 * kBK * 2, st->attr_p3);
+        if (stage <= 32768) return launch(gemm_bf16_tcgen05_persistent_kernel<6>, 6, 32768, st->attr_p6);
+        return launch(gemm_bf16_tcgen05_persistent_kernel<4>, 4, kABytes + 256 * kBK * 2, st->attr_p4);
+    }
     if (c.p.bn <= 128 && c.p.k_blocks * fold <= 3) {
         // very short K loops (conv1: 3 blocks): latency bound per CTA, so two stages and three CTAs per SM
         size_t smem = 2 * stage + 1024;
@@ -350,6 +373,7 @@ int cnn_forward_dev(vpk_ctx* ctx, const uint8_t* d_images, int32_t n, float* d_s
     if (!s || !s->loaded) { set_error("vpk_cnn_forward: call vpk_cnn_load first"); return VPK_ERR_STATE; }
     if (n <= 0) return VPK_OK;
     VPK_TRY(ensure_activations(ctx, n));
+    s->persistent = !(getenv("VPK_GEMM_PERSIST") && atoi(getenv("VPK_GEMM_PERSIST")) == 0);      // A/B switch, default on
     typedef __nv_bfloat16 bf;
     const float* mean = s->has_mean ? s->mean.as<float>() : nullptr;
     {

@@ -355,4 +355,219 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Persistent form: one CTA per SM slot walks the output tiles (m fastest, so neighbouring CTAs share the weight
+// tile in the L2) with TWO accumulators in tensor memory: while the epilogue warps drain tile j from one buffer,
+// the MMA warp accumulates tile j + 1 into the other and the TMA warp is already filling the ring for it.  The
+// shared-memory ring and its phases run on across tiles; barriers are initialised and tensor memory is allocated once
+// per CTA.  No split-K here (the FC layers keep the one-tile-per-CTA kernel above).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int kStages>
+__global__ void __launch_bounds__(kGemmThreads)
+gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
+                                    const int m_tiles, const int n_tiles, const int total_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[kStages], bar_empty[kStages], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_bytes = (uint32_t)p.bn * kBK * 2;
+    const uint32_t sA = sbase, sB = sbase + kStages * kABytes;
+    const int nfold = p.fold > 1 ? p.fold : 1;
+    const int nkb = p.k_blocks;
+    const int per_tile = nkb * nfold;                      // K blocks streamed per tile
+    uint32_t ncols1 = 32;                                  // columns of one accumulator
+    while ((int)ncols1 < p.bn * nfold) ncols1 <<= 1;
+    const uint32_t ncols = 2 * ncols1;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&acc_full[b]), 1); mbar_init(smem_u32(&acc_empty[b]), kGemmThreads - 64); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            uint32_t it = 0;                               // K blocks issued by this CTA so far (ring position)
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int mt = t % m_tiles, rest = t / m_tiles, nt = rest % n_tiles, g = (rest / n_tiles) * nfold;
+                const int m0 = mt * kBM, n0 = nt * p.bn;
+                for (int q = 0; q < per_tile; ++q, ++it) {
+                    const int gi = q / nkb, kb = q - gi * nkb, ge = g + gi;
+                    const int s = (int)(it % kStages);
+                    const uint32_t ph = (it / kStages) & 1u;
+                    mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+                    const uint32_t full = smem_u32(&bar_full[s]);
+                    mbar_expect_tx(full, kABytes + b_bytes);
+                    const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+                    const int kh = tap / p.taps_x, kw = tap - kh * p.taps_x;
+                    tma_load_2d(sA + s * kABytes, &tmA, full, ge * p.a_col_group + cb * kBK, m0 + kh * p.row_pitch + kw);
+                    tma_load_2d(sB + s * b_bytes, &tmB, full, kb * kBK, ge * p.b_row_group + n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = umma_idesc_bf16(kBM, p.bn);
+        uint32_t it = 0, j = 0;                            // ring position, tiles done by this CTA
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+            const uint32_t buf = j & 1u;
+            mbar_wait(smem_u32(&acc_empty[buf]), ((j >> 1) & 1u) ^ 1u);       // the epilogue has drained this accumulator
+            tcgen05_fence_after();
+            const uint32_t tacc = tmem + buf * ncols1;
+            for (int q = 0; q < per_tile; ++q, ++it) {
+                const int gi = q / nkb, i = q - gi * nkb;
+                const int s = (int)(it % kStages);
+                const uint32_t ph = (it / kStages) & 1u;
+                mbar_wait(smem_u32(&bar_full[s]), ph);
+                tcgen05_fence_after();
+                if (lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        uint64_t ad = umma_desc_sw128(sA + s * kABytes + k * 32);
+                        uint64_t bd = umma_desc_sw128(sB + s * b_bytes + k * 32);
+                        tcgen05_mma_bf16(tacc + (uint32_t)(gi * p.bn), ad, bd, idesc, (i | k) ? 1u : 0u);
+                    }
+                    tcgen05_commit(smem_u32(&bar_empty[s]));        // frees the smem stage when the MMAs retire
+                    if (q == per_tile - 1) tcgen05_commit(smem_u32(&acc_full[buf]));
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> bias/ReLU(/LRN) -> global =====
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
+        const int half = (warp - 2) >> 2;             // which half of the tile's columns this warp writes
+        const int row = quarter * 32 + lane;
+        uint32_t j = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+            const int mt = t % m_tiles, rest = t / m_tiles, nt = rest % n_tiles, g = (rest / n_tiles) * nfold;
+            const int m0 = mt * kBM, n0 = nt * p.bn;
+            const uint32_t buf = j & 1u;
+            const uint32_t tacc = tmem + buf * ncols1 + ((uint32_t)(quarter * 32) << 16);
+            const int m = m0 + row;
+            bool valid = m < p.m_total;
+            long long orow = 0;
+            if (valid) {
+                int n = m / p.hp_wp, r = m - n * p.hp_wp;
+                int y = r / p.wp, x = r - y * p.wp;
+                valid = (y < p.h_valid) && (x < p.w_valid);
+                orow = (long long)n * p.out_hp_wp + (long long)(y + p.out_pad) * p.out_wp + (x + p.out_pad);
+            }
+            mbar_wait(smem_u32(&acc_full[buf]), (j >> 1) & 1u);
+            tcgen05_fence_after();
+            const int ccol0 = g * p.c_col_group + n0;
+            if (p.lrn) {
+                const int nch = nfold * p.n_valid;
+                const int cmid = ((nch / 16 + 1) / 2) * 16;
+                const int cb = half ? cmid : 0, ce = half ? nch : cmid;
+                float prev0 = 0.f, prev1 = 0.f, cur[16], nxt[16];
+                auto load_chunk = [&](int c, float (&v)[16]) {
+                    uint32_t r[16];
+                    tmem_ld16(tacc + (uint32_t)c, r);
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) {
+                        float x = __uint_as_float(r[jj]);
+                        if (p.bias) x += __ldg(p.bias + g * p.n_valid + c + jj);
+                        x = p.relu ? fmaxf(x, 0.f) : x;
+                        v[jj] = (c + jj < nch) ? x : 0.f;
+                    }
+                };
+                if (cb > 0) { load_chunk(cb - 16, cur); prev0 = cur[14]; prev1 = cur[15]; }
+                load_chunk(cb, cur);
+                for (int c = cb; c < ce; c += 16) {
+                    const bool more = c + 16 < nch;
+                    if (more) load_chunk(c + 16, nxt);
+                    if (c + 16 >= ce) {                    // last TMEM read of this thread for this tile: hand the accumulator back
+                        tcgen05_fence_before();
+                        mbar_arrive(smem_u32(&acc_empty[buf]));
+                    }
+                    float sq[20];
+                    sq[0] = prev0 * prev0; sq[1] = prev1 * prev1;
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) sq[2 + jj] = cur[jj] * cur[jj];
+                    sq[18] = more ? nxt[0] * nxt[0] : 0.f;
+                    sq[19] = more ? nxt[1] * nxt[1] : 0.f;
+                    if (valid) {
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            const float s0 = sq[2 * jj] + sq[2 * jj + 1] + sq[2 * jj + 2] + sq[2 * jj + 3] + sq[2 * jj + 4];
+                            const float s1 = sq[2 * jj + 1] + sq[2 * jj + 2] + sq[2 * jj + 3] + sq[2 * jj + 4] + sq[2 * jj + 5];
+                            const float y0 = cur[2 * jj] * __powf(1.f + (1e-4f / 5.f) * s0, -0.75f);
+                            const float y1 = cur[2 * jj + 1] * __powf(1.f + (1e-4f / 5.f) * s1, -0.75f);
+                            __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
+                            pk[jj] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldc + ccol0 + c);
+                        o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
+                    prev0 = cur[14]; prev1 = cur[15];
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) cur[jj] = nxt[jj];
+                }
+                if (cb >= ce) { tcgen05_fence_before(); mbar_arrive(smem_u32(&acc_empty[buf])); }          // no channels for this half
+            } else {
+                const int c_lo = half ? ((p.bn / 16 + 1) / 2) * 16 : 0, c_hi = half ? p.bn : ((p.bn / 16 + 1) / 2) * 16;
+                for (int c = c_lo; c < c_hi; c += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(tacc + (uint32_t)c, r);
+                    if (c + 16 >= c_hi) {                  // last TMEM read of this thread for this tile
+                        tcgen05_fence_before();
+                        mbar_arrive(smem_u32(&acc_empty[buf]));
+                    }
+                    if (!valid || n0 + c >= p.n_valid) continue;
+                    float v[16];
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) {
+                        float x = __uint_as_float(r[jj]);
+                        if (p.bias) x += __ldg(p.bias + g * p.n_valid + n0 + c + jj);
+                        v[jj] = p.relu ? fmaxf(x, 0.f) : x;
+                    }
+                    if (p.out_f32) {
+                        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldc + ccol0 + c);
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) o[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+                    } else {
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * jj], v[2 * jj + 1]);
+                            pk[jj] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldc + ccol0 + c);
+                        o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
+                }
+                if (c_lo >= c_hi) { tcgen05_fence_before(); mbar_arrive(smem_u32(&acc_empty[buf])); }      // no columns for this half
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols) : "memory");
+    }
+}
+
 }  // namespace vpk
