@@ -144,6 +144,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// the same load without the wait: the registers may be used only after tmem_ld_wait(r) (which names them, so that the
+// compiler keeps every use behind it); lets the epilogue work on one chunk while the next one is on its way
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+
 template <int kStages>
 __global__ void __launch_bounds__(kGemmThreads)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -242,47 +259,55 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const int nch = nfold * p.n_valid;                 // channels of the pixel (folded groups lie side by side in TMEM)
             const int cmid = ((nch / 16 + 1) / 2) * 16;        // this warp normalises the channels [cb, ce) and peeks two beyond each end
             const int cb = half ? cmid : 0, ce = half ? nch : cmid;
-            float prev0 = 0.f, prev1 = 0.f, cur[16], nxt[16];
-            auto load_chunk = [&](int c, float (&v)[16]) {
-                uint32_t r[16];
-                tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
+            float prev0 = 0.f, prev1 = 0.f, cur[16];
+            uint32_t raw[16];
+            const float* bias = p.bias ? p.bias + g * p.n_valid : nullptr;
+            auto issue = [&](int c) { tmem_ld16_issue(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, raw); };
+            auto finish = [&](int c, float (&v)[16]) {           // bias + ReLU of the chunk that has arrived in raw
+                tmem_ld_wait(raw);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    float x = __uint_as_float(r[j]);
-                    if (p.bias) x += __ldg(p.bias + g * p.n_valid + c + j);
+                    float x = __uint_as_float(raw[j]);
+                    if (bias) x += __ldg(bias + c + j);
                     x = p.relu ? fmaxf(x, 0.f) : x;
                     v[j] = (c + j < nch) ? x : 0.f;
                 }
             };
-            if (cb > 0) { load_chunk(cb - 16, cur); prev0 = cur[14]; prev1 = cur[15]; }
-            load_chunk(cb, cur);
+            if (cb > 0) { issue(cb - 16); finish(cb - 16, cur); prev0 = cur[14]; prev1 = cur[15]; }
+            issue(cb);
+            finish(cb, cur);
             for (int c = cb; c < ce; c += 16) {
                 const bool more = c + 16 < nch;
-                if (more) load_chunk(c + 16, nxt);
+                if (more) issue(c + 16);                          // on its way while this chunk is squared
                 float sq[20];
                 sq[0] = prev0 * prev0; sq[1] = prev1 * prev1;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) sq[2 + j] = cur[j] * cur[j];
+                // channels 0 .. 13 of the chunk need nothing of the next one: normalise them while it arrives
+                uint32_t pk[8];
+                auto norm_pair = [&](int j) {
+                    const float s0 = sq[2 * j] + sq[2 * j + 1] + sq[2 * j + 2] + sq[2 * j + 3] + sq[2 * j + 4];
+                    const float s1 = sq[2 * j + 1] + sq[2 * j + 2] + sq[2 * j + 3] + sq[2 * j + 4] + sq[2 * j + 5];
+                    const float y0 = cur[2 * j] * __powf(1.f + (1e-4f / 5.f) * s0, -0.75f);
+                    const float y1 = cur[2 * j + 1] * __powf(1.f + (1e-4f / 5.f) * s1, -0.75f);
+                    __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
+                    pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                };
+#pragma unroll
+                for (int j = 0; j < 7; ++j) norm_pair(j);
+                float nxt[16];
+                if (more) finish(c + 16, nxt);
                 sq[18] = more ? nxt[0] * nxt[0] : 0.f;
                 sq[19] = more ? nxt[1] * nxt[1] : 0.f;
+                norm_pair(7);
                 if (valid) {
-                    uint32_t pk[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float s0 = sq[2 * j] + sq[2 * j + 1] + sq[2 * j + 2] + sq[2 * j + 3] + sq[2 * j + 4];
-                        const float s1 = sq[2 * j + 1] + sq[2 * j + 2] + sq[2 * j + 3] + sq[2 * j + 4] + sq[2 * j + 5];
-                        const float y0 = cur[2 * j] * __powf(1.f + (1e-4f / 5.f) * s0, -0.75f);
-                        const float y1 = cur[2 * j + 1] * __powf(1.f + (1e-4f / 5.f) * s1, -0.75f);
-                        __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
-                        pk[j] = *reinterpret_cast<uint32_t*>(&h);
-                    }
                     uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldc + ccol0 + c);
                     o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 }
                 prev0 = cur[14]; prev1 = cur[15];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+                for (int j = 0; j < 16; ++j) cur[j] = more ? nxt[j] : 0.f;
             }
         } else
         for (int c = half ? ((p.bn / 16 + 1) / 2) * 16 : 0; c < (half ? p.bn : ((p.bn / 16 + 1) / 2) * 16); c += 16) {
