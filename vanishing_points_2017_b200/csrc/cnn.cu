@@ -24,8 +24,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct CnnState {
     bool loaded = false;
     bool attr2 = false, attr3 = false, attr4 = false;     // dynamic shared-memory opt-in of the two GEMM instantiations: per CONTEXT (device)
-    bool attr_p3 = false, attr_p4 = false, attr_p6 = false;      // ... of the persistent instantiations
-    bool persistent = true;                                  // conv3-5 through the persistent kernel (VPK_GEMM_PERSIST=0: off)
+    bool attr_p3 = false, attr_p4 = false, attr_p6 = false, attr_p1 = false;      // ... of the persistent instantiations
+    bool persistent = true;                                  // the convolutions through the persistent kernel (VPK_GEMM_PERSIST=0: off)
     EncodeTiledFn encode = nullptr;
     // bf16 weight matrices (K-major) and fp32 biases, one per layer conv1..fc8
     DBuf w[8], b[8], mean;
@@ -259,26 +259,35 @@ int launch_gemm(vpk_ctx* ctx, const GemmCall& c) {
     dim3 grid(m_tiles, n_tiles, (c.groups / fold) * ksplit);
     const size_t stage = kABytes + (size_t)c.p.bn * kBK * 2;
     KernelScope ks(ctx, c.name);
-    if (ksplit == 1 && st->persistent && !c.p.lrn) {
-        // persistent CTAs with two accumulators in tensor memory (gemm_tcgen05.cuh): two per SM when both accumulators of
-        // both fit the 512 columns, else one per SM with a deeper ring.  Measured on the YUD batch: conv3 0.219 -> 0.187,
-        // conv4 0.215 -> 0.168, conv5 0.124 -> 0.103 ms.  Not for the layers with the LRN in the epilogue: conv2 needs all
-        // 512 columns for two accumulators, i.e. one CTA = eight epilogue warps per SM, and its epilogue then
-        // limits it (0.458 -> 0.578 ms); conv1 (three K blocks per tile) is unchanged (0.261 / 0.264 ms).
+    if (ksplit == 1 && st->persistent && c.p.lrn && c.p.bn * fold > 128) {
+        // conv2 (LRN epilogue over both groups, 256 columns per tile): persistent with ONE accumulator and two CTAs per SM
+        // (0.429 -> 0.420 ms).  With two accumulators it needs all 512 columns, i.e. one CTA per SM, and that runs at
+        // 0.59 ms -- with 8 or with 16 epilogue warps alike: a single TMA / MMA stream per SM cannot keep the operands coming.
+        const int total = m_tiles * n_tiles * (c.groups / fold);
+        const int ctas = std::min(total, 2 * ctx->num_sms);
+        const size_t smem = 3 * stage + 1024;
+        if (!st->attr_p1) { VPK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_persistent_kernel<3, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (kABytes + 128 * kBK * 2) + 1024)); st->attr_p1 = true; }
+        gemm_bf16_tcgen05_persistent_kernel<3, 8, 1><<<ctas, kGemmThreads, smem, ctx->stream>>>(ma, mb, c.p, m_tiles, n_tiles, total);
+        return check_launch(c.name);
+    }
+    if (ksplit == 1 && st->persistent && (!c.p.lrn || c.p.bn * fold <= 128)) {
+        // persistent CTAs with two accumulators in tensor memory (gemm_tcgen05.cuh): two per SM when the accumulators of
+        // both fit the 512 columns, else one per SM with a deeper ring.  Measured on the YUD batch: conv1 0.247 -> 0.219,
+        // conv3 0.219 -> 0.184, conv4 0.215 -> 0.166, conv5 0.124 -> 0.102 ms.
         int ncols1 = 32;
         while (ncols1 < c.p.bn * fold) ncols1 <<= 1;
         const int total = m_tiles * n_tiles * (c.groups / fold);
         const int per_sm = 2 * ncols1 <= 256 ? 2 : 1;
         const int ctas = std::min(total, per_sm * ctx->num_sms);
-        auto launch = [&](auto kern, int stages, int max_stage, bool& done) -> int {
+        auto launch = [&](auto kern, int stages, int max_stage, int epi_warps, bool& done) -> int {
             const size_t smem = stages * stage + 1024;
             if (!done) { VPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, stages * max_stage + 1024)); done = true; }
-            kern<<<ctas, kGemmThreads, smem, ctx->stream>>>(ma, mb, c.p, m_tiles, n_tiles, total);
+            kern<<<ctas, 64 + 32 * epi_warps, smem, ctx->stream>>>(ma, mb, c.p, m_tiles, n_tiles, total);
             return check_launch(c.name);
         };
-        if (per_sm == 2) return launch(gemm_bf16_tcgen05_persistent_kernel<3>, 3, kABytes + 128 * kBK * 2, st->attr_p3);
-        if (stage <= 32768) return launch(gemm_bf16_tcgen05_persistent_kernel<6>, 6, 32768, st->attr_p6);
-        return launch(gemm_bf16_tcgen05_persistent_kernel<4>, 4, kABytes + 256 * kBK * 2, st->attr_p4);
+        if (per_sm == 2) return launch(gemm_bf16_tcgen05_persistent_kernel<3, 8, 2>, 3, kABytes + 128 * kBK * 2, 8, st->attr_p3);
+        if (stage <= 32768) return launch(gemm_bf16_tcgen05_persistent_kernel<6, 8, 2>, 6, 32768, 8, st->attr_p6);
+        return launch(gemm_bf16_tcgen05_persistent_kernel<4, 8, 2>, 4, kABytes + 256 * kBK * 2, 8, st->attr_p4);
     }
     if (c.p.bn <= 128 && c.p.k_blocks * fold <= 3) {
         // very short K loops (conv1: 3 blocks): latency bound per CTA, so two stages and three CTAs per SM

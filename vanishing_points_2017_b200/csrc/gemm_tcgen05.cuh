@@ -383,17 +383,18 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
 
 // ---------------------------------------------------------------------------
 // Persistent form: one CTA per SM slot walks the output tiles (m fastest, so neighbouring CTAs share the weight
-// tile in the L2) with TWO accumulators in tensor memory: while the epilogue warps drain tile j from one buffer,
+// tile in the L2) with kAccBufs = TWO accumulators in tensor memory: while the epilogue warps drain tile j from one buffer,
 // the MMA warp accumulates tile j + 1 into the other and the TMA warp is already filling the ring for it.  The
 // shared-memory ring and its phases run on across tiles; barriers are initialised and tensor memory is allocated once
-// per CTA.  No split-K here (the FC layers keep the one-tile-per-CTA kernel above).
+// per CTA.  kAccBufs = 1 (a tile that needs 256 columns, two CTAs per SM): the main loop waits for the epilogue, but the
+// ring is refilled for the next tile meanwhile.  No split-K here (the FC layers keep the one-tile-per-CTA kernel above).
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int kStages>
-__global__ void __launch_bounds__(kGemmThreads)
+template <int kStages, int kEpiWarps, int kAccBufs>
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps)
 gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
                                     const int m_tiles, const int n_tiles, const int total_tiles) {
     extern __shared__ uint8_t smem_raw[];
@@ -409,13 +410,13 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
     const int per_tile = nkb * nfold;                      // K blocks streamed per tile
     uint32_t ncols1 = 32;                                  // columns of one accumulator
     while ((int)ncols1 < p.bn * nfold) ncols1 <<= 1;
-    const uint32_t ncols = 2 * ncols1;
+    const uint32_t ncols = kAccBufs * ncols1;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&acc_full[b]), 1); mbar_init(smem_u32(&acc_empty[b]), kGemmThreads - 64); }
+        for (int b = 0; b < kAccBufs; ++b) { mbar_init(smem_u32(&acc_full[b]), 1); mbar_init(smem_u32(&acc_empty[b]), 32 * kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -453,8 +454,8 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
         const uint32_t idesc = umma_idesc_bf16(kBM, p.bn);
         uint32_t it = 0, j = 0;                            // ring position, tiles done by this CTA
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
-            const uint32_t buf = j & 1u;
-            mbar_wait(smem_u32(&acc_empty[buf]), ((j >> 1) & 1u) ^ 1u);       // the epilogue has drained this accumulator
+            const uint32_t buf = j % kAccBufs, use = j / kAccBufs;
+            mbar_wait(smem_u32(&acc_empty[buf]), (use & 1u) ^ 1u);            // the epilogue has drained this accumulator
             tcgen05_fence_after();
             const uint32_t tacc = tmem + buf * ncols1;
             for (int q = 0; q < per_tile; ++q, ++it) {
@@ -479,13 +480,15 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
     } else {
         // ===== epilogue: TMEM -> registers -> bias/ReLU(/LRN) -> global =====
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
-        const int half = (warp - 2) >> 2;             // which half of the tile's columns this warp writes
+        constexpr int kParts = kEpiWarps / 4;         // warps per lane quarter: each takes a range of the tile's columns
+        const int part = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
+        auto part_start = [&](int chunks, int q) { return ((q * chunks + kParts - 1) / kParts) * 16; };     // in columns
         uint32_t j = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
             const int mt = t % m_tiles, rest = t / m_tiles, nt = rest % n_tiles, g = (rest / n_tiles) * nfold;
             const int m0 = mt * kBM, n0 = nt * p.bn;
-            const uint32_t buf = j & 1u;
+            const uint32_t buf = j % kAccBufs, use = j / kAccBufs;
             const uint32_t tacc = tmem + buf * ncols1 + ((uint32_t)(quarter * 32) << 16);
             const int m = m0 + row;
             bool valid = m < p.m_total;
@@ -496,62 +499,68 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
                 valid = (y < p.h_valid) && (x < p.w_valid);
                 orow = (long long)n * p.out_hp_wp + (long long)(y + p.out_pad) * p.out_wp + (x + p.out_pad);
             }
-            mbar_wait(smem_u32(&acc_full[buf]), (j >> 1) & 1u);
+            mbar_wait(smem_u32(&acc_full[buf]), use & 1u);
             tcgen05_fence_after();
             const int ccol0 = g * p.c_col_group + n0;
             if (p.lrn) {
                 const int nch = nfold * p.n_valid;
-                const int cmid = ((nch / 16 + 1) / 2) * 16;
-                const int cb = half ? cmid : 0, ce = half ? nch : cmid;
-                float prev0 = 0.f, prev1 = 0.f, cur[16], nxt[16];
-                auto load_chunk = [&](int c, float (&v)[16]) {
-                    uint32_t r[16];
-                    tmem_ld16(tacc + (uint32_t)c, r);
+                const int cb = part_start(nch / 16, part), ce = part + 1 < kParts ? part_start(nch / 16, part + 1) : nch;
+                float prev0 = 0.f, prev1 = 0.f, cur[16];
+                uint32_t raw[16];
+                const float* bias = p.bias ? p.bias + g * p.n_valid : nullptr;
+                auto issue = [&](int c) { tmem_ld16_issue(tacc + (uint32_t)c, raw); };
+                auto finish = [&](int c, float (&v)[16]) {           // bias + ReLU of the chunk that has arrived in raw
+                    tmem_ld_wait(raw);
 #pragma unroll
                     for (int jj = 0; jj < 16; ++jj) {
-                        float x = __uint_as_float(r[jj]);
-                        if (p.bias) x += __ldg(p.bias + g * p.n_valid + c + jj);
+                        float x = __uint_as_float(raw[jj]);
+                        if (bias) x += __ldg(bias + c + jj);
                         x = p.relu ? fmaxf(x, 0.f) : x;
                         v[jj] = (c + jj < nch) ? x : 0.f;
                     }
                 };
-                if (cb > 0) { load_chunk(cb - 16, cur); prev0 = cur[14]; prev1 = cur[15]; }
-                load_chunk(cb, cur);
+                if (cb > 0) { issue(cb - 16); finish(cb - 16, cur); prev0 = cur[14]; prev1 = cur[15]; }
+                issue(cb);
+                finish(cb, cur);
                 for (int c = cb; c < ce; c += 16) {
                     const bool more = c + 16 < nch;
-                    if (more) load_chunk(c + 16, nxt);
-                    if (c + 16 >= ce) {                    // last TMEM read of this thread for this tile: hand the accumulator back
-                        tcgen05_fence_before();
-                        mbar_arrive(smem_u32(&acc_empty[buf]));
-                    }
+                    if (more) issue(c + 16);
                     float sq[20];
                     sq[0] = prev0 * prev0; sq[1] = prev1 * prev1;
 #pragma unroll
                     for (int jj = 0; jj < 16; ++jj) sq[2 + jj] = cur[jj] * cur[jj];
+                    uint32_t pk[8];
+                    auto norm_pair = [&](int jj) {
+                        const float s0 = sq[2 * jj] + sq[2 * jj + 1] + sq[2 * jj + 2] + sq[2 * jj + 3] + sq[2 * jj + 4];
+                        const float s1 = sq[2 * jj + 1] + sq[2 * jj + 2] + sq[2 * jj + 3] + sq[2 * jj + 4] + sq[2 * jj + 5];
+                        const float y0 = cur[2 * jj] * __powf(1.f + (1e-4f / 5.f) * s0, -0.75f);
+                        const float y1 = cur[2 * jj + 1] * __powf(1.f + (1e-4f / 5.f) * s1, -0.75f);
+                        __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
+                        pk[jj] = *reinterpret_cast<uint32_t*>(&h);
+                    };
+#pragma unroll
+                    for (int jj = 0; jj < 7; ++jj) norm_pair(jj);
+                    float nxt[16];
+                    if (more) finish(c + 16, nxt);
+                    if (c + 16 >= ce) {                    // last TMEM read of this thread for this tile: hand the accumulator back
+                        tcgen05_fence_before();
+                        mbar_arrive(smem_u32(&acc_empty[buf]));
+                    }
                     sq[18] = more ? nxt[0] * nxt[0] : 0.f;
                     sq[19] = more ? nxt[1] * nxt[1] : 0.f;
+                    norm_pair(7);
                     if (valid) {
-                        uint32_t pk[8];
-#pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) {
-                            const float s0 = sq[2 * jj] + sq[2 * jj + 1] + sq[2 * jj + 2] + sq[2 * jj + 3] + sq[2 * jj + 4];
-                            const float s1 = sq[2 * jj + 1] + sq[2 * jj + 2] + sq[2 * jj + 3] + sq[2 * jj + 4] + sq[2 * jj + 5];
-                            const float y0 = cur[2 * jj] * __powf(1.f + (1e-4f / 5.f) * s0, -0.75f);
-                            const float y1 = cur[2 * jj + 1] * __powf(1.f + (1e-4f / 5.f) * s1, -0.75f);
-                            __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
-                            pk[jj] = *reinterpret_cast<uint32_t*>(&h);
-                        }
                         uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldc + ccol0 + c);
                         o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                     }
                     prev0 = cur[14]; prev1 = cur[15];
 #pragma unroll
-                    for (int jj = 0; jj < 16; ++jj) cur[jj] = nxt[jj];
+                    for (int jj = 0; jj < 16; ++jj) cur[jj] = more ? nxt[jj] : 0.f;
                 }
                 if (cb >= ce) { tcgen05_fence_before(); mbar_arrive(smem_u32(&acc_empty[buf])); }          // no channels for this half
             } else {
-                const int c_lo = half ? ((p.bn / 16 + 1) / 2) * 16 : 0, c_hi = half ? p.bn : ((p.bn / 16 + 1) / 2) * 16;
+                const int c_lo = part_start(p.bn / 16, part), c_hi = part + 1 < kParts ? part_start(p.bn / 16, part + 1) : p.bn;
                 for (int c = c_lo; c < c_hi; c += 16) {
                     uint32_t r[16];
                     tmem_ld16(tacc + (uint32_t)c, r);
