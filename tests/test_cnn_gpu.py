@@ -85,3 +85,15 @@ def test_batch_is_deterministic_and_order_independent(cnn):
     a = net.forward_batch(imgs)
     b = net.forward_batch(imgs[::-1].copy())[::-1]
     np.testing.assert_array_equal(a, b)
+
+
+def test_persistent_and_one_tile_gemm_kernels_give_the_same_bits(cnn, monkeypatch):
+    """The convolutions run through the persistent tcgen05 kernel (two accumulators in tensor memory) by default and
+    through the one-tile-per-CTA kernel with VPK_GEMM_PERSIST=0: same MMA order per tile, same epilogue arithmetic."""
+    net = cnn.init_caffe(None, None, 0)
+    imgs = sphere_images(7, seed=11)
+    a = net.forward_batch(imgs)
+    monkeypatch.setenv("VPK_GEMM_PERSIST", "0")
+    b = net.forward_batch(imgs)
+    monkeypatch.delenv("VPK_GEMM_PERSIST")
+    np.testing.assert_array_equal(a, b)
