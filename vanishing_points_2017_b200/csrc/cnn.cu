@@ -154,15 +154,23 @@ __global__ void __launch_bounds__(256) lrn_pool_kernel(const __nv_bfloat16* __re
 #pragma unroll
     for (int dy = 0; dy < 5; ++dy) {
         const int y = y0 + dy;
-        if (y >= H) break;
+        // the five loads of a patch row are issued together (no early exits in between), then reduced
+        uint4 raw[5];
+        bool ok[5];
 #pragma unroll
         for (int dx = 0; dx < 5; ++dx) {
             const int x = x0 + dx;
-            if (x >= W) break;
-            const __nv_bfloat16* p = in + (((long long)n * H + y) * W + x) * C + c0;
+            ok[dx] = y < H && x < W;
+            raw[dx] = make_uint4(0u, 0u, 0u, 0u);
+            if (ok[dx]) raw[dx] = *reinterpret_cast<const uint4*>(in + (((long long)n * H + y) * W + x) * C + c0);
+        }
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) {
+            if (!ok[dx]) continue;
             float v[8];
-            bf16x8_to_float(*reinterpret_cast<const uint4*>(p), v);
+            bf16x8_to_float(raw[dx], v);
             if (kLrn) {
+                const __nv_bfloat16* p = in + (((long long)n * H + y) * W + x0 + dx) * C + c0;
                 float lo0 = 0.f, lo1 = 0.f, hi0 = 0.f, hi1 = 0.f;
                 if (c0 > 0) { float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p - 2)); lo0 = q.x; lo1 = q.y; }
                 if (c0 + 8 < C) { float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p + 8)); hi0 = q.x; hi1 = q.y; }
